@@ -1,0 +1,328 @@
+// Fused link chains, generic-size version: one thread block walks one serial stream.
+//   TX: bits -> Scrambler (per-frame reset) -> mapping -> OFDM_map_carriers -> OFDM_modulator
+//   RX: OFDM_demodulator -> LS_CE -> equalize_signal -> get_payload -> demapping -> DeScrambler -> BER
+// The Nfft = 4096 / N_carrier <= 1024 fast path of the RX chain lives in chain_rx4096.cu.
+#include "fft.cuh"
+#include "interp.cuh"
+
+const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
+#define SLOT_ZERO (-2147483647 - 1)
+#define CH_THREADS 256
+
+template <typename T> struct LinkDev {
+    int Nfft, logN, Tg, Nc, S, SpF, Nd, Np, bps, scramble;
+    int frame_bits, frames;
+    uint32_t prev0;
+    const int32_t* slot;      // Nfft: data rank / -1-pilot / SLOT_ZERO
+    const int32_t* data0;     // Nd 0-based carriers
+    const int32_t* pil0;      // Np 0-based carriers
+    const cx<T>* pilots;      // Np x S column-major
+    const cx<T>* tw;
+    DevConst<T> con;
+};
+
+struct LinkHost {
+    std::vector<int32_t> slot, data0, pil0;
+};
+
+uint32_t ofdm_reg_to_prev(const uint8_t* reg) {
+    uint32_t p = 0;
+    for (int m = 1; m <= 15; ++m) if (reg[m - 1] & 1) p |= 1u << (32 - m);
+    return p;
+}
+
+template <typename T> static int make_linkdev(ofdm_ctx* ctx, const ofdm_link_params* lp, LinkDev<T>& d) {
+    REQUIRE(ctx, lp && lp->Nfft > 0 && is_pow2(lp->Nfft) && lp->S > 0 && lp->SpF > 0 && lp->S % lp->SpF == 0, "bad link parameters (S must be a multiple of SpF)");
+    REQUIRE(ctx, lp->Nfft >= 8 && lp->Nfft <= (ctx->precision == OFDM_PREC_F64 ? 4096 : 8192), "unsupported Nfft");
+    REQUIRE(ctx, lp->Tg >= 0 && lp->Tg <= lp->Nfft && lp->N_carrier >= 2 && lp->N_carrier <= lp->Nfft, "bad Tg / N_carrier");
+    REQUIRE(ctx, lp->Nd >= 1 && lp->Np >= 2 && lp->data_carriers_host && lp->pilot_carriers_host && lp->pilot_vals_host && lp->reg0_host, "missing link tables");
+    ConstTable ct = host_constellation(lp->constellation);
+    REQUIRE(ctx, ct.bps > 0, "unknown constellation");
+    LinkHost h;
+    h.slot.assign(lp->Nfft, SLOT_ZERO);
+    h.data0.resize(lp->Nd); h.pil0.resize(lp->Np);
+    for (int i = 0; i < lp->Nd; ++i) { int c = lp->data_carriers_host[i]; REQUIRE(ctx, c >= 1 && c <= lp->Nfft, "data carrier out of range"); h.slot[c - 1] = i; h.data0[i] = c - 1; }
+    for (int i = 0; i < lp->Np; ++i) { int c = lp->pilot_carriers_host[i]; REQUIRE(ctx, c >= 1 && c <= lp->Nfft, "pilot carrier out of range"); h.slot[c - 1] = -1 - i; h.pil0[i] = c - 1; }
+    d.Nfft = lp->Nfft; d.logN = ilog2(lp->Nfft); d.Tg = lp->Tg; d.Nc = lp->N_carrier; d.S = lp->S; d.SpF = lp->SpF; d.Nd = lp->Nd; d.Np = lp->Np;
+    d.bps = ct.bps; d.scramble = lp->scramble;
+    d.frame_bits = lp->SpF * lp->Nd * ct.bps; d.frames = lp->S / lp->SpF;
+    d.prev0 = ofdm_reg_to_prev(lp->reg0_host);
+    d.slot = (const int32_t*)ctx_blob(ctx, h.slot.data(), sizeof(int32_t) * h.slot.size());
+    d.data0 = (const int32_t*)ctx_blob(ctx, h.data0.data(), sizeof(int32_t) * h.data0.size());
+    d.pil0 = (const int32_t*)ctx_blob(ctx, h.pil0.data(), sizeof(int32_t) * h.pil0.size());
+    d.pilots = (const cx<T>*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, (size_t)lp->Np * lp->S);
+    d.tw = (const cx<T>*)ctx_twiddles(ctx, lp->Nfft);
+    d.con = make_devconst<T>(lp->constellation);
+    REQUIRE(ctx, d.slot && d.data0 && d.pil0 && d.pilots && d.tw, "device upload failed");
+    return OFDM_OK;
+}
+
+// 32 bits of a shared-memory bit array starting at bit `pos` (words beyond nwords read as 0)
+__device__ __forceinline__ uint32_t sm_get32(const uint32_t* w, int pos, int nwords) {
+    if (pos < 0) {  // bits before the array read as 0
+        if (pos <= -32) return 0u;
+        return w[0] << (-pos);
+    }
+    int wi = pos >> 5, sh = pos & 31;
+    uint32_t lo = wi < nwords ? w[wi] : 0u;
+    uint32_t hi = (sh && wi + 1 < nwords) ? w[wi + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+
+// ------------------------------------------------------------------------------------ TX
+template <typename T>
+__global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, const uint32_t* __restrict__ bits, int64_t total_bits, cx<T>* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using C = cx<T>;
+    C* a = (C*)smem_raw;
+    C* bbuf = a + p.Nfft;
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint32_t* s0 = (uint32_t*)(bbuf + p.Nfft);
+    uint32_t* s1 = s0 + fw;
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    for (int f = 0; f < p.frames; ++f) {
+        const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+        for (int w = tid; w < fw; w += CH_THREADS) {
+            uint32_t v = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+            if (w == 0 && p.scramble) v ^= (p.prev0 >> 19) ^ (p.prev0 >> 18);   // fold the register pre-history into the input
+            s0[w] = v;
+        }
+        __syncthreads();
+        uint32_t* cur = s0; uint32_t* nxt = s1;
+        if (p.scramble) {
+            // s = in' * prod_j (1 + x^(13*2^j) + x^(14*2^j)) over GF(2), 13*2^j < frame_bits  (SURVEY KAT 2)
+            for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
+                for (int w = tid; w < fw; w += CH_THREADS)
+                    nxt[w] = cur[w] ^ sm_get32(cur, 32 * w - sh13, fw) ^ sm_get32(cur, 32 * w - sh14, fw);
+                __syncthreads();
+                uint32_t* t = cur; cur = nxt; nxt = t;
+            }
+        }
+        for (int sf = 0; sf < p.SpF; ++sf) {
+            const int s = f * p.SpF + sf;
+            for (int k = tid; k < p.Nfft; k += CH_THREADS) {
+                int sl = p.slot[k];
+                C v = mk<T>(0, 0);
+                if (sl >= 0) {
+                    int q = sf * p.Nd + sl;                       // QAM symbol number inside the frame
+                    uint32_t g = sm_get32(cur, q * p.bps, fw);
+                    int idx = 0;
+                    for (int i = 0; i < p.bps; ++i) idx = (idx << 1) | ((g >> i) & 1u);
+                    v = mk<T>(p.con.re[idx], p.con.im[idx]);
+                } else if (sl != SLOT_ZERO) v = p.pilots[(int64_t)s * p.Np + (-1 - sl)];
+                a[k] = v;
+            }
+            __syncthreads();
+            C* r = block_fft<T, true>(a, bbuf, p.Nfft, p.logN, p.tw);
+            const T scale = (T)1 / (T)p.Nfft;
+            C* dst = out + (b * p.S + s) * (int64_t)(p.Nfft + p.Tg);
+            for (int i = tid; i < p.Nfft; i += CH_THREADS) {
+                C v = cscale(r[i], scale);
+                dst[p.Tg + i] = v;
+                if (i >= p.Nfft - p.Tg) dst[i - (p.Nfft - p.Tg)] = v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, bits && time && B >= 0, "bad argument");
+    if (B == 0) return OFDM_OK;
+    DISPATCH_T(ctx, {
+        LinkDev<T> d;
+        int rc = make_linkdev<T>(ctx, lp, d);
+        if (rc) return rc;
+        size_t smem = 2 * sizeof(cx<T>) * d.Nfft + 2 * sizeof(uint32_t) * ((d.frame_bits + 31) / 32);
+        auto k = tx_chain_kernel<T>;
+        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (cx<T>*)time);
+    });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ------------------------------------------------------------------------------------ RX (generic)
+template <typename T>
+__global__ void __launch_bounds__(CH_THREADS) rx_chain_kernel(LinkDev<T> p, PlanDev<T> plan, const cx<T>* __restrict__ rx, const uint32_t* __restrict__ txbits,
+                                                              int64_t total_bits, uint32_t* __restrict__ outbits, cx<T>* __restrict__ Hout,
+                                                              unsigned long long* __restrict__ counts, int32_t* __restrict__ err_stream, T near_eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using C = cx<T>;
+    __shared__ int red_i[32];
+    C* a = (C*)smem_raw;
+    C* bbuf = a + p.Nfft;
+    C* y = bbuf + p.Nfft;
+    C* dk = y + plan.n_knots;
+    C* Hs = dk + plan.n_knots;                       // Nc
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint32_t* raw = (uint32_t*)(Hs + p.Nc);          // fw words of demapped bits
+    uint8_t* symidx = (uint8_t*)(raw + fw);          // SpF*Nd decided constellation indices of the frame
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    int errs = 0, nears = 0;
+    for (int s = 0; s < p.S; ++s) {
+        const C* src = rx + (b * p.S + s) * (int64_t)(p.Nfft + p.Tg) + p.Tg;
+        for (int i = tid; i < p.Nfft; i += CH_THREADS) a[i] = src[i];
+        __syncthreads();
+        C* r = block_fft<T, false>(a, bbuf, p.Nfft, p.logN, p.tw);
+        if (s == 0) {   // LS_CE: first symbol only (`LS_CE.m:27-31`)
+            for (int k = tid; k < p.Np; k += CH_THREADS) y[plan.ext_lo + k] = cdiv(r[p.pil0[k]], p.pilots[k]);
+            __syncthreads();
+            plan_apply(plan, y, dk, Hs);
+            __syncthreads();
+            if (Hout) for (int k = tid; k < p.Nc; k += CH_THREADS) Hout[b * p.Nc + k] = Hs[k];
+        }
+        const int sf = s % p.SpF;
+        for (int dr = tid; dr < p.Nd; dr += CH_THREADS) {   // equalize_signal + get_payload + demapping decision
+            int c = p.data0[dr];
+            C e = (c < p.Nc) ? cdiv(r[c], Hs[c]) : mk<T>(0, 0);   // rows beyond N_carrier are zeros (`equalize_signal.m:3`)
+            T margin;
+            int idx = nearest_idx(p.con, e.x, e.y, &margin);
+            if (margin < near_eps) ++nears;
+            symidx[sf * p.Nd + dr] = (uint8_t)idx;
+        }
+        __syncthreads();
+        if (sf == p.SpF - 1) {   // frame complete: pack bits, DeScrambler, compare
+            const int f = s / p.SpF;
+            for (int w = tid; w < fw; w += CH_THREADS) {
+                const int b0 = 32 * w, b1 = min(b0 + 32, p.frame_bits);
+                uint32_t word = 0;
+                for (int q = b0 / p.bps; q * p.bps < b1; ++q) {
+                    int idx = symidx[q];
+                    for (int i = 0; i < p.bps; ++i) {
+                        int pos = q * p.bps + i;
+                        if (pos >= b0 && pos < b1 && ((idx >> (p.bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                    }
+                }
+                raw[w] = word;
+            }
+            __syncthreads();
+            const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+            for (int w = tid; w < fw; w += CH_THREADS) {
+                uint32_t cur = raw[w];
+                uint32_t o = cur;
+                if (p.scramble) {
+                    uint32_t prev = w ? raw[w - 1] : p.prev0;
+                    o = cur ^ ((cur << 13) | (prev >> 19)) ^ ((cur << 14) | (prev >> 18));
+                }
+                const int n = min(32, p.frame_bits - 32 * w);
+                if (n < 32) o &= (1u << n) - 1u;
+                if (txbits) {
+                    uint32_t t = bits_get32(txbits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+                    errs += __popc(o ^ t);
+                }
+                if (outbits) bits_put(outbits, base + 32 * (int64_t)w, n, o);
+            }
+            __syncthreads();
+        }
+    }
+    errs = block_sum(errs, red_i);
+    nears = block_sum(nears, red_i);
+    if (tid == 0) {
+        if (counts) {
+            if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+            atomicAdd(&counts[1], (unsigned long long)stream_bits);
+            if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+        }
+        if (err_stream) err_stream[b] = errs;
+    }
+}
+
+int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, const uint32_t* tx_bits, uint32_t* out_bits,
+                           void* H, int64_t* counts, int32_t* err_stream, double near_eps, bool* handled);
+
+extern "C" int ofdm_rx_chain_t5(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, const uint32_t* tx_bits, uint32_t* out_bits,
+                                void* H, int64_t* counts, int32_t* err_stream, double near_eps) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, rx && B >= 0 && lp, "bad argument");
+    if (B == 0) return OFDM_OK;
+    bool handled = false;
+    int rc = ofdm_rx_chain_fast4096(ctx, lp, rx, B, tx_bits, out_bits, H, counts, err_stream, near_eps, &handled);
+    if (rc || handled) return rc;
+    DISPATCH_T(ctx, {
+        LinkDev<T> d;
+        rc = make_linkdev<T>(ctx, lp, d);
+        if (rc) return rc;
+        const InterpPlan* pl = ctx_plan(ctx, lp->pilot_carriers_host, lp->Np, lp->N_carrier, nullptr, lp->N_carrier, OFDM_INTERP_SPLINE);
+        REQUIRE(ctx, pl != nullptr, "plan construction failed");
+        for (int i = 0; i < lp->Np; ++i) REQUIRE(ctx, lp->pilot_carriers_host[i] <= lp->N_carrier, "pilot beyond N_carrier");
+        const int64_t stream_bits = (int64_t)d.frame_bits * d.frames;
+        if (out_bits && (stream_bits % 32 != 0 || d.frame_bits % 32 != 0))
+            CUDA_TRY(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t) * OFDM_BIT_WORDS(B * stream_bits), ctx->stream));
+        const int fw = (d.frame_bits + 31) / 32;
+        size_t smem = sizeof(cx<T>) * (2 * (size_t)d.Nfft + 2 * (size_t)pl->n_knots + d.Nc) + sizeof(uint32_t) * fw + (size_t)d.SpF * d.Nd + 16;
+        auto k = rx_chain_kernel<T>;
+        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, plan_dev<T>(pl), (const cx<T>*)rx, tx_bits, B * stream_bits, out_bits, (cx<T>*)H,
+                                                           (unsigned long long*)counts, err_stream, (T)near_eps);
+    });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ------------------------------------------------------------------------------------ RX from host buffers
+extern "C" int ofdm_rx_chain_t5_host(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx_host, int64_t B, const uint32_t* tx_bits_host,
+                                     uint32_t* out_bits_host, void* H_host, int64_t* counts_host, int64_t chunk) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, rx_host && lp && B >= 0 && counts_host, "bad argument");
+    ConstTable ct = host_constellation(lp->constellation);
+    REQUIRE(ctx, ct.bps > 0, "unknown constellation");
+    const size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
+    const int64_t stream_bits = (int64_t)lp->S * lp->Nd * ct.bps;
+    REQUIRE(ctx, stream_bits % 32 == 0, "host-buffer chain needs word-aligned streams (stream bits % 32 == 0)");
+    const int64_t words = stream_bits / 32;
+    const int64_t L = (int64_t)lp->S * (lp->Nfft + lp->Tg);
+    if (chunk <= 0) chunk = 2048;
+    chunk = std::min<int64_t>(chunk, std::max<int64_t>(B, 1));
+    // per-slot device staging: rx | tx bits | out bits | H
+    const size_t rx_b = esz * L * chunk, bits_b = sizeof(uint32_t) * words * chunk, H_b = esz * lp->N_carrier * chunk;
+    const size_t slot_b = rx_b + 2 * bits_b + H_b + 256;
+    if (ctx->staging_bytes < slot_b) {
+        for (int i = 0; i < 2; ++i) { if (ctx->staging[i]) cudaFree(ctx->staging[i]); ctx->staging[i] = nullptr; }
+        for (int i = 0; i < 2; ++i) CUDA_TRY(ctx, cudaMalloc(&ctx->staging[i], slot_b));
+        ctx->staging_bytes = slot_b;
+    }
+    int64_t* counts_d = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void**)&counts_d, 3 * sizeof(int64_t)));
+    CUDA_TRY(ctx, cudaMemsetAsync(counts_d, 0, 3 * sizeof(int64_t), ctx->stream));
+    cudaStream_t user = ctx->stream;
+    cudaEvent_t done[2] = {ctx->ev[0], ctx->ev[1]};
+    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], user));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream[i], ctx->ev[2], 0));
+    int rc = OFDM_OK;
+    int64_t launches = 0;
+    for (int64_t c0 = 0, it = 0; c0 < B && rc == OFDM_OK; c0 += chunk, ++it) {
+        const int slot = (int)(it & 1);
+        const int64_t nb = std::min(chunk, B - c0);
+        cudaStream_t st = ctx->copy_stream[slot];   // each slot is a self-contained in-order pipeline: H2D -> kernel -> D2H
+        unsigned char* base = (unsigned char*)ctx->staging[slot];
+        void* rx_d = base;
+        uint32_t* tx_d = (uint32_t*)(base + rx_b);
+        uint32_t* ob_d = (uint32_t*)(base + rx_b + bits_b);
+        void* H_d = base + rx_b + 2 * bits_b;
+        CUDA_TRY(ctx, cudaMemcpyAsync(rx_d, (const unsigned char*)rx_host + esz * L * c0, esz * L * nb, cudaMemcpyHostToDevice, st));
+        if (tx_bits_host) CUDA_TRY(ctx, cudaMemcpyAsync(tx_d, tx_bits_host + words * c0, sizeof(uint32_t) * words * nb, cudaMemcpyHostToDevice, st));
+        ctx->stream = st;
+        int64_t l0 = ctx->launches;
+        rc = ofdm_rx_chain_t5(ctx, lp, rx_d, nb, tx_bits_host ? tx_d : nullptr, out_bits_host ? ob_d : nullptr, H_host ? H_d : nullptr, counts_d, nullptr, 0.0);
+        launches += ctx->launches - l0;
+        ctx->stream = user;
+        if (rc) break;
+        if (out_bits_host) CUDA_TRY(ctx, cudaMemcpyAsync(out_bits_host + words * c0, ob_d, sizeof(uint32_t) * words * nb, cudaMemcpyDeviceToHost, st));
+        if (H_host) CUDA_TRY(ctx, cudaMemcpyAsync((unsigned char*)H_host + esz * lp->N_carrier * c0, H_d, esz * lp->N_carrier * nb, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(ctx, cudaEventRecord(done[slot], st));
+    }
+    for (int i = 0; i < 2; ++i) { cudaStreamSynchronize(ctx->copy_stream[i]); }
+    (void)launches;
+    if (rc == OFDM_OK) {
+        cudaError_t e = cudaMemcpy(counts_host, counts_d, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "counter read-back failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(counts_d);
+    return rc;
+}

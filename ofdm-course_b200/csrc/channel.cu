@@ -1,0 +1,180 @@
+// add_STO / add_CFO / Noise / get_MP_channel_resp + conv -- impairments on B x L serial streams.
+#include "fft.cuh"
+#include "philox.cuh"
+
+// ---- add_STO (`Task 5/add_STO.m:5-9`)
+template <typename T>
+__global__ void add_sto_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const int32_t* __restrict__ nsto, cx<T>* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    int64_t b = i / L, n = i - b * L;
+    int64_t src = n + (int64_t)nsto[b];
+    out[i] = (src >= 0 && src < L) ? in[b * L + src] : mk<T>(0, 0);
+}
+extern "C" int ofdm_add_sto(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const int32_t* nsto, void* out) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, in && out && nsto && B >= 0 && L >= 0 && in != out, "bad argument (in-place not supported)");
+    if (B * L == 0) return OFDM_OK;
+    DISPATCH_T(ctx, { add_sto_kernel<T><<<(unsigned)cdiv64(B * L, 256), 256, 0, ctx->stream>>>((const cx<T>*)in, B, L, nsto, (cx<T>*)out); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ---- add_CFO (`Task 5/add_CFO.m:6-7`): y .* exp(2j*pi*CFO*n/Nfft).  The phase is range-reduced
+// in double (frac of CFO*n/Nfft) so FP32 streams of 64K samples keep full accuracy.
+template <typename T>
+__global__ void add_cfo_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const double* __restrict__ cfo, double inv_nfft,
+                               cx<T>* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    int64_t b = i / L, n = i - b * L;
+    double ph = cfo[b] * (double)n * inv_nfft;
+    ph -= floor(ph);
+    double s, c;
+    sincospi(2.0 * ph, &s, &c);
+    out[i] = cmul(in[i], mk<T>((T)c, (T)s));
+}
+extern "C" int ofdm_add_cfo(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const double* cfo, int Nfft, void* out) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, in && out && cfo && B >= 0 && L >= 0 && Nfft > 0, "bad argument");
+    if (B * L == 0) return OFDM_OK;
+    DISPATCH_T(ctx, { add_cfo_kernel<T><<<(unsigned)cdiv64(B * L, 256), 256, 0, ctx->stream>>>((const cx<T>*)in, B, L, cfo, 1.0 / Nfft, (cx<T>*)out); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ---- Noise (`Task 5/Noise.m:3-11`): mean power over the whole stream (double), then
+// sqrt(P/2)*(N1 + 1i*N2).  N1/N2 imported (real block, imaginary block) or Philox.
+template <typename T>
+__global__ void stream_power_kernel(const cx<T>* __restrict__ in, int64_t L, double* __restrict__ power_sum) {
+    __shared__ double red[32];
+    const int64_t b = blockIdx.x;
+    double s = 0;
+    for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
+        cx<T> v = in[b * L + n];
+        s += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(&power_sum[b], s);
+}
+template <typename T>
+__global__ void add_noise_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const double* __restrict__ snr_db,
+                                 const double* __restrict__ power_sum, const T* __restrict__ normals, uint64_t seed,
+                                 int64_t first_stream, cx<T>* __restrict__ out, double* __restrict__ nvar) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * L) return;
+    int64_t b = i / L, n = i - b * L;
+    double P = power_sum[b] / (double)L;
+    double np = P / pow(10.0, snr_db[b] / 10.0);
+    T sigma = (T)sqrt(np / 2);
+    T g1, g2;
+    if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
+    else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
+    cx<T> v = in[i];
+    out[i] = mk<T>(v.x + sigma * g1, v.y + sigma * g2);
+    if (nvar && n == 0) nvar[b] = sqrt(np);
+}
+extern "C" int ofdm_add_noise(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const double* snr_db, const void* normals,
+                              uint64_t seed, int64_t first_stream_id, void* out, double* nvar) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, in && out && snr_db && B >= 0 && L >= 0, "bad argument");
+    if (B * L == 0) return OFDM_OK;
+    double* psum = (double*)ctx_scratch(ctx, sizeof(double) * B);
+    REQUIRE(ctx, psum != nullptr, "scratch allocation failed");
+    CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
+    int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
+    DISPATCH_T(ctx, {
+        stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, psum);
+        ctx->launches++;
+        add_noise_kernel<T><<<(unsigned)cdiv64(B * L, 256), 256, 0, ctx->stream>>>((const cx<T>*)in, B, L, snr_db, psum, (const T*)normals, seed,
+                                                                                    first_stream_id, (cx<T>*)out, nvar);
+    });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ---- get_MP_channel_resp (`Task 5/get_MP_channel_resp.m:2-19`)
+template <typename T>
+__global__ void load_real_taps_kernel(const double* __restrict__ h, int D, int N, cx<T>* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N) out[i] = mk<T>(i < D ? (T)h[i] : (T)0, (T)0);
+}
+extern "C" int ofdm_mp_channel_resp(ofdm_ctx* ctx, const double* taps, int K, int Nfft, double* h_host, int h_cap, int* h_len, void* H_dev) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, taps && K > 0 && h_host && h_len, "bad argument");
+    int max_delay = 0;
+    for (int i = 0; i < K; ++i) { REQUIRE(ctx, taps[2 * i] >= 0, "negative delay"); max_delay = std::max(max_delay, (int)taps[2 * i]); }
+    int D = max_delay + 1;
+    REQUIRE(ctx, D <= h_cap, "h_host too small");
+    for (int i = 0; i < D; ++i) h_host[i] = 0;
+    for (int i = 0; i < K; ++i) h_host[(int)taps[2 * i]] = taps[2 * i + 1];  // later rows overwrite (:14)
+    *h_len = D;
+    if (H_dev) {
+        REQUIRE(ctx, D <= Nfft, "impulse response longer than Nfft");  // fft(h, Nfft) would truncate
+        const double* hd = (const double*)ctx_blob(ctx, h_host, sizeof(double) * D);
+        REQUIRE(ctx, hd != nullptr, "device upload failed");
+        size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
+        void* tmp = ctx_scratch(ctx, esz * Nfft);
+        REQUIRE(ctx, tmp != nullptr, "scratch allocation failed");
+        DISPATCH_T(ctx, { load_real_taps_kernel<T><<<(Nfft + 255) / 256, 256, 0, ctx->stream>>>(hd, D, Nfft, (cx<T>*)tmp); });
+        LAUNCH_CHECK(ctx);
+        return ofdm_fft(ctx, tmp, H_dev, 1, Nfft, 0);
+    }
+    return OFDM_OK;
+}
+
+// ---- conv(x, h, 'full')(1:L) (`Task 5/Main_model_Task_5.m:126-127`): short FIR, taps in shared memory.
+template <typename T>
+__global__ void fir_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const cx<T>* __restrict__ h, int D, int per_stream,
+                           cx<T>* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* hs = (cx<T>*)smem_raw;
+    const int64_t b = blockIdx.x;
+    const cx<T>* hb = per_stream ? h + b * D : h;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) hs[d] = hb[d];
+    __syncthreads();
+    for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
+        cx<T> acc = mk<T>(0, 0);
+        const cx<T>* x = in + b * L;
+        int dmax = (int)min((int64_t)D - 1, n);
+        for (int d = 0; d <= dmax; ++d) {
+            cx<T> t = hs[d];
+            if (t.x != (T)0 || t.y != (T)0) acc = acc + cmul(x[n - d], t);   // sparse taps: skip exact zeros
+        }
+        out[b * L + n] = acc;
+    }
+}
+extern "C" int ofdm_apply_fir(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const void* h, int D, int per_stream, void* out) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, in && out && h && B >= 0 && L >= 0 && D > 0 && in != out, "bad argument (in-place not supported)");
+    REQUIRE(ctx, D <= 4096, "FIR longer than 4096 taps");
+    if (B * L == 0) return OFDM_OK;
+    int bx = (int)std::min<int64_t>(cdiv64(L, 256), 256);
+    DISPATCH_T(ctx, {
+        fir_kernel<T><<<dim3((unsigned)B, bx), 256, sizeof(cx<T>) * D, ctx->stream>>>((const cx<T>*)in, B, L, (const cx<T>*)h, D, per_stream, (cx<T>*)out);
+    });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ---- fused Task-5 channel: AWGN then FIR (`Task 5/Main_model_Task_5.m:108,123-127`).
+extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const void* normals,
+                               uint64_t seed, int64_t first_stream_id, const void* h, int D, void* rx) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, tx && rx && B >= 0 && L >= 0, "bad argument");
+    if (B * L == 0) return OFDM_OK;
+    size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
+    if (snr_db && h) {
+        // noise must precede the filter; stage the noisy stream in a second buffer region
+        void* tmp = nullptr;
+        CUDA_TRY(ctx, cudaMallocAsync(&tmp, esz * B * L, ctx->stream));
+        int rc = ofdm_add_noise(ctx, tx, B, L, snr_db, normals, seed, first_stream_id, tmp, nullptr);
+        if (!rc) rc = ofdm_apply_fir(ctx, tmp, B, L, h, D, 0, rx);
+        cudaFreeAsync(tmp, ctx->stream);
+        return rc;
+    }
+    if (snr_db) return ofdm_add_noise(ctx, tx, B, L, snr_db, normals, seed, first_stream_id, rx, nullptr);
+    if (h) return ofdm_apply_fir(ctx, tx, B, L, h, D, 0, rx);
+    CUDA_TRY(ctx, cudaMemcpyAsync(rx, tx, esz * B * L, cudaMemcpyDeviceToDevice, ctx->stream));
+    return OFDM_OK;
+}

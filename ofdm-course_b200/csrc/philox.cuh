@@ -1,0 +1,28 @@
+// Counter-based RNG for throughput runs: Philox4x32-10 keyed by (seed), counter = (stream id, sample
+// index), so a stream's noise is identical for any batch split or GPU count.
+// The reference's `normrnd` stream (`Task 5/Noise.m:7-8`) is MATLAB-only; parity runs import normals.
+#pragma once
+#include <stdint.h>
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+        uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+        uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += W0; k1 += W1;
+    }
+}
+// two independent unit normals for (stream, sample): Box-Muller on two 32-bit uniforms in (0,1]
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t stream, uint64_t n, float& g1, float& g2) {
+    uint32_t c[4] = {(uint32_t)n, (uint32_t)(n >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
+    float u2 = (float)c[1] * 2.3283064365386963e-10f;            // [0,1)
+    float r = sqrtf(-2.0f * __logf(u1));
+    float s, co;
+    __sincosf(6.283185307179586f * u2, &s, &co);
+    g1 = r * co; g2 = r * s;
+}

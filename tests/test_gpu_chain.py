@@ -1,0 +1,155 @@
+"""GPU parity of the fused chains (TX, Task-5 channel, M1 RX chain) against the oracle's script-level
+restatement, plus size-independent properties at larger batch."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import chains as OC
+
+pytestmark = pytest.mark.gpu
+TAPS5 = [[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]]
+
+
+@pytest.fixture(scope="module")
+def G():
+    import ofdm_b200
+    return ofdm_b200
+
+
+def rel_err(a, b):
+    return np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / max(np.linalg.norm(np.asarray(b).ravel()), 1e-300)
+
+
+def _lp(ctx, p, scramble=True):
+    return ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers,
+                           p.pilotCarriers, p.pilotValues, scramble=scramble)
+
+
+PARAMS = {
+    "t5_comb4": lambda: OC.params_task5(comb=4),
+    "t5_comb7": lambda: OC.params_task5(comb=7),
+    "t4": lambda: OC.params_task4(),
+    "t4_8psk": lambda: OC.params_task4(Constellation="8PSK"),
+    "t4_bpsk": lambda: OC.params_task4(Constellation="BPSK"),
+}
+
+
+@pytest.mark.parametrize("name", list(PARAMS))
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_tx_chain_matches_oracle(G, name, prec):
+    p = PARAMS[name]()
+    ctx = G.default_context(prec)
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(1)
+    B = 3
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    tx = ctx.tx_chain(lp, ctx.bits(bits.ravel()), B).cpu().numpy().reshape(B, -1)
+    for b in range(B):
+        ref, _, _ = OC.tx_chain(p, bits[b])
+        assert rel_err(tx[b], ref) < (1e-12 if prec == "f64" else 2e-6)
+
+
+@pytest.mark.parametrize("name", list(PARAMS))
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_rx_chain_matches_oracle(G, name, prec):
+    p = PARAMS[name]()
+    ctx = G.default_context(prec)
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(2)
+    B = 3
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    h, _ = O.get_MP_channel_resp(TAPS5, p.Nfft)
+    normals = rng.standard_normal((B, 2, p.stream_len))
+    rxs, refs = [], []
+    for b in range(B):
+        t, _, _ = OC.tx_chain(p, bits[b])
+        r = OC.channel_task5(p, t, 18.0, TAPS5, normals=normals[b])
+        rxs.append(r)
+        refs.append(OC.rx_chain_task5(p, r, bits[b]))
+    rx_d = ctx.cplx(np.stack(rxs).reshape(B, p.N_symb, p.Nfft + p.T_Guard))
+    res = ctx.rx_chain_t5(lp, rx_d, B, tx_bits_dev=ctx.bits(bits.ravel()), near_eps=1e-3 if prec == "f32" else 1e-9, want_err_per_stream=True)
+    ctx.sync()
+    H = res["H"].cpu().numpy()
+    got_bits = ctx.host_bits(res["bits"], B * p.stream_bits).reshape(B, -1)
+    counts = res["counts"].cpu().numpy()
+    eps = res["err_per_stream"].cpu().numpy()
+    mism = 0
+    for b in range(B):
+        assert rel_err(H[b], refs[b]["H"]) < (1e-10 if prec == "f64" else 2e-5)
+        mism += int(np.sum(got_bits[b] != refs[b]["bits"]))
+        assert eps[b] == int(np.sum(got_bits[b] != bits[b]))
+    ref_err = sum(r["errors"] for r in refs)
+    assert counts[1] == B * p.stream_bits
+    assert counts[0] == int(np.sum(got_bits != bits))
+    if prec == "f64":
+        assert mism == 0 and counts[0] == ref_err
+    else:
+        # FP32 decisions may differ only for symbols within epsilon of a boundary; each flips <= bps
+        # decided bits, which the descrambler spreads to <= 3*bps
+        assert mism <= 3 * p.bps * counts[2]
+        assert abs(int(counts[0]) - ref_err) <= mism
+
+
+def test_rx_chain_noise_free_loopback_ber_zero(G):
+    """SURVEY KAT 3 through the fused chains at a larger batch: BER = 0 without impairments."""
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(3)
+    B = 64
+    bits = rng.integers(0, 2, B * p.stream_bits).astype(np.uint8)
+    bd = ctx.bits(bits)
+    tx = ctx.tx_chain(lp, bd, B)
+    res = ctx.rx_chain_t5(lp, tx, B, tx_bits_dev=bd)
+    counts = res["counts"].cpu().numpy()
+    assert counts[0] == 0 and counts[1] == B * p.stream_bits
+    assert np.array_equal(ctx.host_bits(res["bits"], B * p.stream_bits), bits)
+    H = res["H"].cpu().numpy()
+    assert np.max(np.abs(H - 1)) < 1e-4
+
+
+def test_channel_t5_device_matches_oracle_and_philox_is_batch_invariant(G):
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f64")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(4)
+    B = 2
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    h, _ = O.get_MP_channel_resp(TAPS5, p.Nfft)
+    normals = rng.standard_normal((B, 2, p.stream_len))
+    tx = ctx.tx_chain(lp, ctx.bits(bits.ravel()), B)
+    rx = ctx.channel_t5(tx, snr_db=20.0, h_dev=ctx.cplx(h), normals_dev=ctx.real(normals, ctx.rdtype)).cpu().numpy().reshape(B, -1)
+    for b in range(B):
+        t, _, _ = OC.tx_chain(p, bits[b])
+        ref = OC.channel_task5(p, t, 20.0, TAPS5, normals=normals[b])
+        assert rel_err(rx[b], ref) < 1e-12
+    # counter-based noise: stream k gets the same realisation whatever the batch split
+    c32 = G.default_context("f32")
+    lp32 = _lp(c32, p)
+    tx32 = c32.tx_chain(lp32, c32.bits(bits.ravel()), B)
+    full = c32.channel_t5(tx32, snr_db=20.0, seed=77, first_stream_id=10).cpu().numpy()
+    second = c32.channel_t5(tx32[1:2].contiguous(), snr_db=20.0, seed=77, first_stream_id=11).cpu().numpy()
+    assert np.array_equal(full[1], second[0])
+
+
+def test_rx_chain_host_entry(G):
+    import torch
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(5)
+    B = 10
+    bits = rng.integers(0, 2, B * p.stream_bits).astype(np.uint8)
+    bd = ctx.bits(bits)
+    tx = ctx.tx_chain(lp, bd, B)
+    rx = ctx.channel_t5(tx, snr_db=15.0, h_dev=ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0]), seed=5)
+    dev = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd)
+    ctx.sync()
+    rx_h = rx.cpu().pin_memory()
+    tb_h = bd.cpu().pin_memory()
+    ob_h = torch.zeros_like(tb_h).pin_memory()
+    H_h = torch.zeros((B, p.N_carrier), dtype=torch.complex64).pin_memory()
+    counts = ctx.rx_chain_t5_host(lp, rx_h, B, tb_h, ob_h, H_h, chunk=4)   # 3 chunks, ragged last one
+    dc = dev["counts"].cpu().numpy()
+    assert counts[0] == dc[0] and counts[1] == dc[1]
+    assert torch.equal(ob_h, dev["bits"].cpu()) and torch.equal(H_h, dev["H"].cpu())

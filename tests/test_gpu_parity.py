@@ -1,0 +1,359 @@
+"""GPU parity: every reference-named function of ofdm_b200 (through the C ABI) against the float64
+oracle on the same seeded inputs.  Tolerances: bits / indices exact (except decisions within a stated
+epsilon of a boundary, which are counted); FP32 results within REL32 relative L2 / max error."""
+import numpy as np
+import pytest
+
+import oracle as O
+from oracle import chains as OC
+
+pytestmark = pytest.mark.gpu
+
+REL32 = 2e-5      # FP32 relative tolerance for spectra / estimates (about 1e-6*log2(Nfft) expected)
+REL64 = 1e-11     # FP64 mode
+
+
+@pytest.fixture(scope="module")
+def G():
+    import ofdm_b200
+    return ofdm_b200
+
+
+def rel_err(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    return np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300)
+
+
+def crandn(rng, *shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+TAPS5 = [[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]]
+TAPS4 = [[0, 1], [4, .6], [10, .3]]
+
+
+# ------------------------------------------------------------------ a1/a2
+@pytest.mark.parametrize("L", [1, 13, 14, 15, 31, 32, 33, 64, 700, 6640, 21504])
+def test_scrambler_bit_exact(G, L):
+    rng = np.random.default_rng(L)
+    x = rng.integers(0, 2, L).astype(np.uint8)
+    for reg in (O.DEFAULT_REGISTER, rng.integers(0, 2, 15).astype(np.uint8)):
+        s_ref, r_ref = O.Scrambler(reg, x)
+        s, r = G.Scrambler(reg, x)
+        assert np.array_equal(s, s_ref) and np.array_equal(r, r_ref)
+        d_ref, rd_ref = O.DeScrambler(reg, s_ref)
+        d, rd = G.DeScrambler(reg, s_ref)
+        assert np.array_equal(d, d_ref) and np.array_equal(d, x) and np.array_equal(rd, rd_ref)
+
+
+def test_scrambler_kat_and_batched_frames(G):
+    s, _ = G.Scrambler(O.DEFAULT_REGISTER, np.zeros(32, dtype=np.uint8))
+    assert "".join(map(str, s)) == "00000111111011000010000011010001"   # SURVEY KAT 1
+    ctx = G.default_context()
+    rng = np.random.default_rng(5)
+    for nf, L in [(10, 6640), (7, 21504), (33, 100)]:
+        x = rng.integers(0, 2, nf * L).astype(np.uint8)
+        ref = np.concatenate([O.Scrambler(O.DEFAULT_REGISTER, x[i * L:(i + 1) * L])[0] for i in range(nf)])
+        out = ctx.host_bits(ctx.scramble(ctx.bits(x), nf, L), nf * L)
+        assert np.array_equal(out, ref)
+        back = ctx.host_bits(ctx.scramble(ctx.bits(ref), nf, L, descramble=True), nf * L)
+        assert np.array_equal(back, x)
+
+
+def test_scrambler_empty(G):
+    ctx = G.default_context()
+    import torch
+    out = ctx.scramble(torch.zeros(1, dtype=torch.int32, device=ctx.device), 0, 0)
+    assert out.numel() == 1
+
+
+# ------------------------------------------------------------------ a3-a5
+@pytest.mark.parametrize("name", ["BPSK", "QPSK", "8PSK", "16QAM"])
+def test_constellation_mapping_demapping(G, name):
+    d_ref, bps_ref = O.constellation_func(name)
+    d, bps = G.constellation_func(name)
+    assert bps == bps_ref and np.max(np.abs(d - d_ref)) < 1e-15
+    rng = np.random.default_rng(3)
+    for n in (1201, 1200, 7, 64):
+        bits = rng.integers(0, 2, n).astype(np.uint8)
+        iq_ref, pad_ref = O.mapping(bits, name)
+        for prec, tol in (("f32", 1e-7), ("f64", 1e-15)):
+            iq, pad = G.mapping(bits, name, precision=prec)
+            assert pad == pad_ref and np.max(np.abs(iq - iq_ref)) < tol
+            assert np.array_equal(G.demapping(pad, iq, name, precision=prec), bits)
+    # noisy points: decisions equal the oracle's except within epsilon of a boundary
+    iq = iq_ref[:300] + 0.3 * crandn(rng, 300)
+    ref = O.demapping(-1, iq, name)
+    got = G.demapping(-1, iq, name, precision="f64")
+    assert np.array_equal(got, ref)
+    got32 = G.demapping(-1, iq.astype(np.complex64), name)
+    assert np.array_equal(got32, O.demapping(-1, iq.astype(np.complex64), name))
+
+
+def test_demapping_tie_and_nan(G):
+    assert list(G.demapping(-1, np.array([0 + 0j]), "16QAM")) == [0, 1, 0, 1]
+    assert list(G.demapping(-1, np.array([np.nan + 0j]), "16QAM")) == [0, 0, 0, 0]
+
+
+# ------------------------------------------------------------------ a6-a9
+def test_map_carriers_mod_demod_payload(G):
+    rng = np.random.default_rng(7)
+    for p in (OC.params_task4(), OC.params_task5(comb=4)):
+        iq = crandn(rng, len(p.dataCarriers) * p.N_symb)
+        ref = O.OFDM_map_carriers(iq, p.N_symb, p.Nfft, p.dataCarriers, p.pilotCarriers, p.pilotValues)
+        got = G.OFDM_map_carriers(iq, p.N_symb, p.Nfft, p.dataCarriers, p.pilotCarriers, p.pilotValues, precision="f64")
+        assert np.max(np.abs(got - ref)) == 0
+        t_ref = O.OFDM_modulator(ref, p.T_Guard)
+        for prec, tol in (("f32", REL32), ("f64", REL64)):
+            t = G.OFDM_modulator(ref, p.T_Guard, precision=prec)
+            assert t.shape == t_ref.shape and rel_err(t, t_ref) < tol
+            y = G.OFDM_demodulator(t_ref, p.T_Guard, precision=prec)
+            assert rel_err(y, O.OFDM_demodulator(t_ref, p.T_Guard)) < tol
+        pay = G.get_payload(ref, p.dataCarriers, precision="f64")
+        assert np.array_equal(pay, O.get_payload(ref, p.dataCarriers))
+    # scalar pilot broadcast (Task 3 quirk) and the v1 mapper of Task 1
+    p = OC.params_task4()
+    iq = crandn(rng, 332 * 50)
+    assert np.max(np.abs(G.OFDM_map_carriers(iq, 50, 1024, p.dataCarriers, p.pilotCarriers, 1.7, precision="f64")
+                         - O.OFDM_map_carriers(iq, 50, 1024, p.dataCarriers, p.pilotCarriers, 1.7))) == 0
+    pil, data = O.pilot_layout_percent(400, 25, 1024, last_gap=2)
+    iq = crandn(rng, len(data) * 50)
+    assert np.max(np.abs(G.OFDM_map_carriers_v1(iq, 50, 1024, data, pil, 2.68, precision="f64")
+                         - O.OFDM_map_carriers_v1(iq, 50, 1024, data, pil, 2.68))) < 1e-15
+
+
+@pytest.mark.parametrize("N", [8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+def test_fft_sizes(G, N):
+    rng = np.random.default_rng(N)
+    x = crandn(rng, 3, N)
+    for prec, tol in (("f32", REL32), ("f64", REL64)):
+        if prec == "f64" and N > 4096:
+            continue
+        ctx = G.default_context(prec)
+        assert rel_err(ctx.fft(ctx.cplx(x)).cpu().numpy(), np.fft.fft(x, axis=1)) < tol
+        assert rel_err(ctx.fft(ctx.cplx(x), inverse=True).cpu().numpy(), np.fft.ifft(x, axis=1)) < tol
+
+
+# ------------------------------------------------------------------ a10-a13
+def test_sto_cfo_noise_channel(G):
+    rng = np.random.default_rng(11)
+    y = crandn(rng, 5000)
+    for n in (0, 1, 37, 4999, 5000, -1, -300):
+        assert np.allclose(G.add_STO(y, n, precision="f64"), O.add_STO(y, n), atol=0)
+    for cfo in (0.0, 0.24, 7.24, 30.5, -3.1):
+        assert rel_err(G.add_CFO(y, cfo, 1024, precision="f64"), O.add_CFO(y, cfo, 1024)) < 1e-12
+    long = crandn(rng, 64512)
+    assert rel_err(G.add_CFO(long, 30.49, 4096), O.add_CFO(long, 30.49, 4096)) < 3e-7   # range-reduced phase in FP32
+    normals = rng.standard_normal((2, 5000))
+    ref, nv_ref = O.Noise(20, y, normals=normals)
+    got, nv = G.Noise(20, y, normals=normals, precision="f64")
+    assert rel_err(got, ref) < 1e-13 and abs(nv - nv_ref) < 1e-12
+    got32, nv32 = G.Noise(20, y, normals=normals)
+    assert rel_err(got32, ref) < 1e-6
+    # Philox noise: right power, zero mean, independent parts
+    clean = np.ones(200000, dtype=complex)
+    noisy, nv = G.Noise(10, clean, seed=123)
+    e = noisy - clean
+    assert abs(np.mean(np.abs(e) ** 2) - 0.1) < 2e-3 and abs(np.mean(e)) < 3e-3 and abs(nv - np.sqrt(0.1)) < 1e-6
+    assert abs(np.mean(e.real * e.imag)) < 1e-3
+    h_ref, H_ref = O.get_MP_channel_resp(TAPS5, 4096)
+    h, H = G.get_MP_channel_resp(TAPS5, 4096, precision="f64")
+    assert np.array_equal(h, h_ref) and rel_err(H, H_ref) < 1e-13
+    assert rel_err(G.apply_channel(y, h_ref, precision="f64"), O.apply_channel(y, h_ref)) < 1e-14
+    assert rel_err(G.apply_channel(y, h_ref), O.apply_channel(y, h_ref)) < 1e-6
+
+
+# ------------------------------------------------------------------ a14-a16
+def _task4_rx(rng, sto, cfo, snr=None, taps=None):
+    p = OC.params_task4()
+    bits = rng.integers(0, 2, p.stream_bits).astype(np.uint8)
+    tx, _, _ = OC.tx_chain(p, bits)
+    rx = OC.impair_task4(p, tx, SNR_dB=snr, Time_Delay=sto, Freq_Shift=cfo, taps=taps, rng=rng)
+    return p, bits, rx
+
+
+@pytest.mark.parametrize("sto,cfo,snr", [(0, 0.0, None), (37, 7.24, None), (300, 25.24, 25), (900, 0.24, 25), (1152, 12.4, 30)])
+def test_autocorr_and_ifo(G, sto, cfo, snr):
+    rng = np.random.default_rng(13)
+    p, bits, rx = _task4_rx(rng, sto, cfo, snr)
+    ac_ref, tg_ref, fo_ref = O.AutoCorrFunction(rx, p.T_Guard, p.Nfft)
+    for prec, tol in (("f32", 2e-5), ("f64", 1e-10)):
+        ac, tg, fo = G.AutoCorrFunction(rx, p.T_Guard, p.Nfft, precision=prec)
+        ok = np.isfinite(ac_ref)
+        assert np.array_equal(np.isnan(ac.real), np.isnan(ac_ref.real))
+        assert np.max(np.abs(ac[ok] - ac_ref[ok])) < tol
+        assert tg == tg_ref and abs(fo - fo_ref) < tol
+    r = O.add_CFO(O.add_STO(O.add_STO(rx, tg_ref), -(p.Nfft + p.T_Guard)), -fo_ref, p.Nfft)
+    fixed_ref, ifo_ref = O.remove_IFO(r, p.Nfft)
+    fixed, ifo = G.remove_IFO(r, p.Nfft)
+    assert ifo == ifo_ref == round(cfo) and rel_err(fixed, fixed_ref) < 1e-6
+
+
+def test_autocorr_fallback_and_ifo_failure(G):
+    rng = np.random.default_rng(14)
+    x = crandn(rng, 4000)
+    ac, tg, fo = G.AutoCorrFunction(x, 128, 1024)
+    ac_ref, tg_ref, fo_ref = O.AutoCorrFunction(x, 128, 1024)
+    assert tg == tg_ref == 65 and abs(fo - fo_ref) < 1e-5
+    with pytest.raises(IndexError):
+        G.remove_IFO(0.001 * x, 1024)
+    ctx = G.default_context()
+    _, _, _, fail = ctx.cp_autocorr(ctx.cplx(x)[None], 128, 1024)
+    assert int(fail[0]) == 1
+
+
+@pytest.mark.parametrize("sto,cfo", [(37, 7.24), (900, 0.24), (0, 0.0)])
+def test_fine_sync(G, sto, cfo):
+    rng = np.random.default_rng(15)
+    p, bits, rx = _task4_rx(rng, sto, cfo, 30)
+    ac, tg, fo = O.AutoCorrFunction(rx, p.T_Guard, p.Nfft)
+    r = O.add_CFO(O.add_STO(O.add_STO(rx, tg), -(p.Nfft + p.T_Guard)), -fo, p.Nfft)
+    r, _ = O.remove_IFO(r, p.Nfft)
+    Y = O.OFDM_demodulator(r.reshape((1152, 50), order="F"), 128)
+    ref, tau_ref, ph_ref = O.fine_sync(Y, p.pilotCarriers, p.pilotValues, 1, 1, return_estimates=True)
+    got, tau, ph = G.fine_sync(Y, p.pilotCarriers, p.pilotValues, 1, 1, return_estimates=True, precision="f64")
+    assert abs(tau - tau_ref) < 1e-12 and abs(ph - ph_ref) < 1e-10 and rel_err(got, ref) < 1e-10
+    got32, tau32, ph32 = G.fine_sync(Y, p.pilotCarriers, p.pilotValues, 1, 1, return_estimates=True)
+    assert abs(tau32 - tau_ref) < 1e-7 and abs(ph32 - ph_ref) < 1e-4 and rel_err(got32, ref) < 2e-4
+    only_t = G.fine_sync(Y, p.pilotCarriers, p.pilotValues, 1, 0, precision="f64")
+    assert rel_err(only_t, O.fine_sync(Y, p.pilotCarriers, p.pilotValues, 1, 0)) < 1e-10
+
+
+# ------------------------------------------------------------------ a17-a21
+def _task5_Y(rng, comb, snr=20, scale=2.0, alternate=True):
+    p = OC.params_task5(comb=comb, scale=scale, alternate=alternate)
+    bits = rng.integers(0, 2, p.stream_bits).astype(np.uint8)
+    if len(p.dataCarriers):
+        tx, _, _ = OC.tx_chain(p, bits)
+    else:
+        grid = np.zeros((p.Nfft, p.N_symb), dtype=complex)
+        grid[p.pilotCarriers - 1, :] = p.pilotValues
+        tx = O.OFDM_modulator(grid, p.T_Guard).ravel(order="F")
+    rx = OC.channel_task5(p, tx, snr, TAPS5, rng=rng)
+    Y = O.OFDM_demodulator(rx.reshape((p.Nfft + p.T_Guard, p.N_symb), order="F"), p.T_Guard)
+    return p, bits, rx, Y
+
+
+@pytest.mark.parametrize("comb", [4, 5, 7, 16, 256, 1])
+def test_ls_ce_interpolate_equalize(G, comb):
+    rng = np.random.default_rng(17 + comb)
+    if comb == 1:
+        p = OC.LinkParams()
+        p.pilotCarriers, p.dataCarriers = O.pilot_layout_percent(1024, 100, 4096, last_gap=1)
+        p.pilotValues, _ = OC.make_pilot_values(1024, 14, "16QAM", 4 / 3, False)
+        Y = crandn(rng, 4096, 14)
+    else:
+        p, bits, rx, Y = _task5_Y(rng, comb)
+    ref = O.LS_CE(Y, p.pilotValues, p.pilotCarriers, p.N_carrier)
+    for prec, tol in (("f32", REL32), ("f64", REL64)):
+        got = G.LS_CE(Y, p.pilotValues, p.pilotCarriers, p.N_carrier, precision=prec)
+        assert got.shape == (1024,) and rel_err(got, ref) < tol
+    Hp = crandn(rng, len(p.pilotCarriers))
+    for method in ("spline", "linear"):
+        r = O.interpolate(Hp, p.pilotCarriers, 1024, method)
+        assert rel_err(G.interpolate(Hp, p.pilotCarriers, 1024, method, precision="f64"), r) < REL64
+        assert rel_err(G.interpolate(Hp, p.pilotCarriers, 1024, method), r) < REL32
+    eq_ref = O.equalize_signal(Y, ref, p.N_carrier)
+    eq = G.equalize_signal(Y, ref, p.N_carrier, precision="f64")
+    assert rel_err(eq, eq_ref) < 1e-13 and np.all(eq[1024:] == 0)
+
+
+def test_interpolate_random_pilots_and_small_counts(G):
+    rng = np.random.default_rng(19)
+    for Np in (2, 3, 4, 17, 40, 256):
+        loc = np.sort(rng.permutation(1024)[:Np]) + 1
+        Hp = crandn(rng, Np)
+        r = O.interpolate(Hp, loc, 1024, "spline")
+        assert rel_err(G.interpolate(Hp, loc, 1024, "spline", precision="f64"), r) < 1e-9
+        assert rel_err(G.interpolate(Hp, loc, 1024, "spline"), r) < 1e-4
+
+
+def test_estimate_channel(G):
+    rng = np.random.default_rng(21)
+    p, bits, rx = _task4_rx(rng, None, None, 25, TAPS4)
+    Y = O.OFDM_demodulator(rx.reshape((1152, 50), order="F"), 128)
+    H_ref, Hp_ref = O.estimate_channel(Y, np.arange(1, 1025), p.pilotCarriers, p.pilotValues)
+    H, Hp = G.estimate_channel(Y, np.arange(1, 1025), p.pilotCarriers, p.pilotValues, precision="f64")
+    assert rel_err(Hp, Hp_ref) < 1e-13 and rel_err(H[:400], H_ref[:400]) < 1e-11 and rel_err(H, H_ref) < 1e-9
+    H32, Hp32 = G.estimate_channel(Y, np.arange(1, 1025), p.pilotCarriers, p.pilotValues)
+    assert rel_err(Hp32, Hp_ref) < 1e-6 and rel_err(H32[:400], H_ref[:400]) < REL32
+
+
+@pytest.mark.parametrize("comb,snr", [(4, 20), (16, 10), (1, 20), (1, 30)])
+def test_mmse_ce(G, comb, snr):
+    rng = np.random.default_rng(23 + comb)
+    if comb == 1:
+        p, bits, rx, Y = _task5_Y(rng, 1, snr=snr, scale=4 / 3, alternate=False)
+    else:
+        p, bits, rx, Y = _task5_Y(rng, comb, snr=snr)
+    h = np.fft.ifft(O.LS_CE(Y, p.pilotValues, p.pilotCarriers, p.N_carrier))
+    ref = O.MMSE_CE(Y, p.pilotValues, p.pilotCarriers, p.Nfft, p.N_carrier, h, snr)
+    got = G.MMSE_CE(Y, p.pilotValues, p.pilotCarriers, p.Nfft, p.N_carrier, h, snr, precision="f64")
+    assert rel_err(got, ref) < 1e-8
+    got32 = G.MMSE_CE(Y, p.pilotValues, p.pilotCarriers, p.Nfft, p.N_carrier, h, snr)
+    assert rel_err(got32, ref) < 5e-5
+
+
+# ------------------------------------------------------------------ a22/a23
+def test_omp_mp_kat5_and_noisy(G):
+    rng = np.random.default_rng(29)
+    # SURVEY KAT 5: static channel, no noise, comb 1
+    p, bits, rx, Y = _task5_Y(rng, 1, snr=None, scale=4 / 3, alternate=False)
+    amp = abs(p.pilotValues[0, 0])
+    A = O.sensing_matrix_dft(p.pilotCarriers, p.Nfft, 1024)
+    y = Y[p.pilotCarriers - 1, 0] / amp
+    H_ref, h_ref, idx_ref = O.OMP_estimate(y, A, p.Nfft, 6, 20)
+    assert list(idx_ref) == [1, 5, 11, 16, 21, 27]
+    for prec, tol in (("f64", 1e-9), ("f32", 2e-4)):
+        H, h, idx = G.OMP_estimate(y, A, p.Nfft, 6, 20, precision=prec)
+        assert list(idx) == list(idx_ref) and rel_err(h, h_ref) < tol and rel_err(H, H_ref) < tol
+        Hm, hm = G.MP_estimate(y, A, p.Nfft, 6, precision=prec)
+        Hm_ref, hm_ref = O.MP_estimate(y, A, p.Nfft, 6)
+        assert np.array_equal(np.nonzero(hm)[0], np.nonzero(hm_ref)[0]) and rel_err(hm, hm_ref) < tol and rel_err(Hm, Hm_ref) < tol
+    # noisy, comb 4 (Np 256, Ldict 1024), dense and partial-DFT descriptor paths agree with the oracle
+    p, bits, rx, Y = _task5_Y(rng, 4, snr=20)
+    A = O.sensing_matrix_dft(p.pilotCarriers, p.Nfft, 1024)
+    y = Y[p.pilotCarriers - 1, 0] / p.pilotValues[:, 0]
+    H_ref, h_ref, idx_ref = O.OMP_estimate(y, A, p.Nfft, 9, 20)
+    Hm_ref, hm_ref = O.MP_estimate(y, A, p.Nfft, 9)
+    ctx = G.default_context("f64")
+    H, h, idx = G.OMP_estimate(y, A, p.Nfft, 9, 20, precision="f64")
+    assert list(idx) == list(idx_ref) and rel_err(H, H_ref) < 1e-9
+    Hd, hd, idxd, it = ctx.omp(ctx.cplx(y)[None], p.Nfft, 9, Ldict=1024, pilot_loc=p.pilotCarriers)
+    n = int(it[0])
+    assert list(idxd[0, :n].cpu().numpy()) == list(idx_ref) and rel_err(Hd[0].cpu().numpy(), H_ref) < 1e-9
+    Hm, hm = G.MP_estimate(y, A, p.Nfft, 9, precision="f64")
+    assert rel_err(Hm, Hm_ref) < 1e-9
+    Hmd, hmd, _ = ctx.mp(ctx.cplx(y)[None], p.Nfft, 9, Ldict=1024, pilot_loc=p.pilotCarriers)
+    assert rel_err(Hmd[0].cpu().numpy(), Hm_ref) < 1e-9
+    H32, h32, idx32 = G.OMP_estimate(y, A, p.Nfft, 9, 20)
+    assert list(idx32) == list(idx_ref) and rel_err(H32, H_ref) < 1e-4
+
+
+def test_omp_random_pilots_large_dictionary(G):
+    rng = np.random.default_rng(31)
+    pil = np.sort(rng.permutation(1024)[:256]) + 1      # `Task5_part2.m:63`
+    htrue = np.zeros(4096, dtype=complex)
+    htrue[[0, 7, 19, 44, 90]] = crandn(rng, 5) * np.array([1, .8, .6, .4, .3])
+    y = np.fft.fft(htrue)[pil - 1] + 0.01 * crandn(rng, 256)
+    A = O.sensing_matrix_dft(pil, 4096, 4096)
+    H_ref, h_ref, idx_ref = O.OMP_estimate(y, A, 4096, 7, 20)
+    ctx = G.default_context("f32")
+    Hd, hd, idxd, it = ctx.omp(ctx.cplx(y)[None], 4096, 7, Ldict=4096, pilot_loc=pil)
+    n = int(it[0])
+    assert list(idxd[0, :n].cpu().numpy()) == list(idx_ref) and rel_err(hd[0].cpu().numpy(), h_ref) < 1e-4
+    H, h, idx = G.OMP_estimate(y, A, 4096, 7, 20)
+    assert list(idx) == list(idx_ref) and rel_err(H, H_ref) < 1e-4
+
+
+# ------------------------------------------------------------------ a24/a25
+def test_ber_mer(G):
+    rng = np.random.default_rng(37)
+    for n in (1, 31, 32, 33, 127, 128, 129, 66400, 1000003):
+        a = rng.integers(0, 2, n).astype(np.uint8)
+        b = a ^ (rng.random(n) < 0.1)
+        assert G.BER_func(a, b) == O.BER_func(a, b)
+    d, _ = O.constellation_func("16QAM")
+    iq = d[rng.integers(0, 16, 5000)] + 0.05 * crandn(rng, 5000)
+    assert abs(G.MER_func(iq, "16QAM", precision="f64") - O.MER_func(iq, "16QAM")) < 1e-10
+    assert abs(G.MER_func(iq, "16QAM") - O.MER_func(iq, "16QAM")) < 1e-4
