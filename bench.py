@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""bench.py -- OFDM symbols/s through the full Task-5 RX chain (workload M1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--streams B]
+
+One "step" = one pass of the fused RX chain (OFDM_demodulator -> LS_CE -> equalize_signal ->
+get_payload -> demapping -> DeScrambler -> BER count) over a batch of B synthetic streams of 14 OFDM
+symbols (Nfft 4096, CP 512, 1024 carriers, comb-4 pilots, 16QAM, 6-tap multipath + AWGN 20 dB)
+that is already resident in HBM.  `value` is device-timed whole-job throughput; `e2e` is the same
+chain through the host-buffer C-ABI entry (pinned host memory, H2D + D2H inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, NumPy float64 -- MATLAB and
+Octave do not exist on the box) on all host cores.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+TAPS5 = [[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]]
+A_M1 = 34121.0           # algorithmic bytes per OFDM symbol (SURVEY 8d / DESIGN.md): 8*4096 + 768 + 8192/14
+SNR_DB = 20.0
+METRIC = "OFDM symbols/s, full Task-5 RX chain"
+WORKLOAD = "M1: Task-5 RX chain, Nfft 4096, CP 512, Nc 1024, comb 4 (Np 256, Nd 768), 16QAM, 14 symbols/stream, 6-tap + AWGN 20 dB"
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_chain_worker(args):
+    """One bounded sample of the workload through the oracle on one host process."""
+    seed, n_streams = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import oracle as O
+    from oracle import chains as OC
+    p = OC.params_task5(comb=4)
+    rng = np.random.default_rng(seed)
+    rxs, bits = [], []
+    for _ in range(n_streams):                         # untimed: build the inputs
+        b = rng.integers(0, 2, p.stream_bits).astype(np.uint8)
+        tx, _, _ = OC.tx_chain(p, b, fast=True)
+        rxs.append(OC.channel_task5(p, tx, SNR_DB, TAPS5, rng=rng))
+        bits.append(b)
+    t0 = time.perf_counter()
+    errs = 0
+    for r, b in zip(rxs, bits):
+        errs += OC.rx_chain_task5(p, r, b, fast=True)["errors"]
+    return time.perf_counter() - t0, n_streams * p.N_symb, errs
+
+
+def cpu_baseline(n_proc, streams_per_proc, seed=1234):
+    """Oracle throughput on `n_proc` host processes (wall clock over the slowest worker)."""
+    import multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    if n_proc == 1:
+        res = [cpu_chain_worker((seed, streams_per_proc))]
+    else:
+        with ctxm.Pool(n_proc) as pool:
+            res = pool.map(cpu_chain_worker, [(seed + i, streams_per_proc) for i in range(n_proc)])
+    wall = max(r[0] for r in res)
+    syms = sum(r[1] for r in res)
+    return syms / wall, syms, wall, time.perf_counter() - t0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1])); mx.append(float(s[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n_proc = os.cpu_count() or 1
+    per_proc = args.ref_streams
+    vals = []
+    for _ in range(args.warmup):
+        pass  # the oracle has no warm-up state worth timing; keep the run short
+    for _ in range(max(1, min(args.steps, 3))):
+        v, syms, wall, _ = cpu_baseline(n_proc, per_proc)
+        vals.append((v, syms, wall))
+    v = float(np.median([x[0] for x in vals]))
+    line = {"metric": METRIC, "value": v, "unit": "symbols/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0,
+            "ms_per_step": 1e3 * float(np.median([x[2] for x in vals])), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "note": "NumPy float64 restatement of the reference (oracle/), MATLAB/Octave absent"},
+            "cpu_baseline": {"value": v, "unit": "symbols/s", "cores": n_proc, "kind": "port",
+                             "sample": f"{n_proc} processes x {per_proc} streams x 14 symbols per step"},
+            "e2e": {"value": v, "unit": "symbols/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ofdm_b200 as G
+    import oracle as O
+    from oracle import chains as OC
+
+    torch.cuda.set_device(local_rank)
+    ctx = G.Context(local_rank, "f32")
+    p = OC.params_task5(comb=4)
+    lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers,
+                         p.pilotCarriers, p.pilotValues)
+    B = args.streams
+    S = p.N_symb
+    words = p.stream_bits // 32
+    dev = ctx.device
+    # ---- synthetic inputs, generated on the device in chunks (TX chain + Task-5 channel)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1000 + rank)
+    tx_bits = torch.randint(-2**31, 2**31 - 1, (B * words,), dtype=torch.int32, device=dev, generator=gen)
+    rx = torch.empty((B, S, p.Nfft + p.T_Guard), dtype=torch.complex64, device=dev)
+    h_dev = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
+    chunk = min(B, 2048)
+    for c0 in range(0, B, chunk):
+        nb = min(chunk, B - c0)
+        tx = ctx.tx_chain(lp, tx_bits[c0 * words:(c0 + nb) * words], nb)
+        ctx.channel_t5(tx, snr_db=SNR_DB, h_dev=h_dev, seed=42, first_stream_id=rank * B + c0, out=rx[c0:c0 + nb].reshape(nb, -1))
+        del tx
+    out_bits = torch.empty(B * words, dtype=torch.int32, device=dev)
+    H = torch.empty((B, p.N_carrier), dtype=torch.complex64, device=dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=tx_bits, out_bits=out_bits, H=H, counts=counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    counts.zero_()
+    l0 = ctx.launches
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    if world > 1:
+        dist.all_reduce(counts)             # the chain's only collective: int64 error / bit counters
+    barrier()
+    launches = ctx.launches - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    # keep the GPU busy a little longer so the clock sampler sees load even for very short runs
+    t_end = time.time() + 1.0
+    while rank == 0 and time.time() < t_end and len(sampler.samples) < 8:
+        step()
+        torch.cuda.synchronize()
+    sampler.stop_flag = True
+    syms_per_step = B * S
+    value = world * syms_per_step * args.steps / (total_ms * 1e-3)
+    cnt = counts.cpu().numpy()
+
+    # ---- e2e: host buffers through the C-ABI host entry (H2D of rx + tx bits, D2H of bits + H + counters)
+    Be = min(B, args.e2e_streams)
+    rx_h = torch.empty((Be, S, p.Nfft + p.T_Guard), dtype=torch.complex64).pin_memory()
+    rx_h.copy_(rx[:Be])
+    tb_h = torch.empty(Be * words, dtype=torch.int32).pin_memory()
+    tb_h.copy_(tx_bits[:Be * words])
+    ob_h = torch.empty(Be * words, dtype=torch.int32).pin_memory()
+    H_h = torch.empty((Be, p.N_carrier), dtype=torch.complex64).pin_memory()
+    torch.cuda.synchronize()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ctx.rx_chain_t5_host(lp, rx_h, Be, tb_h, ob_h, H_h, chunk=args.e2e_chunk)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        c_host = ctx.rx_chain_t5_host(lp, rx_h, Be, tb_h, ob_h, H_h, chunk=args.e2e_chunk)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * Be * S * e2e_steps / e2e_s
+    h2d = rx_h.numel() * 8 + tb_h.numel() * 4
+    d2h = ob_h.numel() * 4 + H_h.numel() * 8 + 24
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    k_ms = float(np.mean(kernel_ms))
+    achieved = A_M1 * syms_per_step / (k_ms * 1e-3) / 1e9
+    traffic = load_traffic()
+    line = {
+        "metric": METRIC, "value": value, "unit": "symbols/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "streams_per_gpu": B, "symbols_per_step_per_gpu": syms_per_step,
+                   "input_bytes_per_gpu": int(rx.numel() * 8), "l2_policy": "inputs (33.8 GB at the default batch) larger than L2; no flush needed",
+                   "noise": "Philox4x32-10 keyed by global stream id", "e2e_streams": Be, "e2e_chunk_streams": args.e2e_chunk,
+                   "ber": float(cnt[0]) / max(float(cnt[1]), 1.0)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_val, "unit": "symbols/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "kernel": "rx4096_kernel<true>", "algorithmic_bytes_per_symbol": A_M1, "kernel_ms": k_ms},
+    }
+    if world == 1 and not args.no_cpu:
+        n_proc = os.cpu_count() or 1
+        v, syms, wall, tot = cpu_baseline(n_proc, args.ref_streams)
+        line["cpu_baseline"] = {"value": v, "unit": "symbols/s", "cores": n_proc, "kind": "port",
+                                "sample": f"{n_proc} processes x {args.ref_streams} streams x 14 symbols of the same workload "
+                                          f"({syms} symbols, {wall:.1f} s of RX-chain time; NumPy float64 oracle, vectorised descrambler)"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU per step (M1: 65,536 = 917,504 symbols)")
+    ap.add_argument("--e2e-streams", type=int, default=4096)
+    ap.add_argument("--e2e-chunk", type=int, default=512)
+    ap.add_argument("--ref-streams", type=int, default=24, help="streams per host process in the CPU sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -62,7 +62,7 @@ typedef struct ofdm_ctx ofdm_ctx;
 OFDM_API int ofdm_ctx_create(ofdm_ctx** out, int device, int precision);
 OFDM_API void ofdm_ctx_destroy(ofdm_ctx* ctx);
 OFDM_API const char* ofdm_last_error(const ofdm_ctx* ctx);
-OFDM_API int ofdm_ctx_set_stream(ofdm_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = own stream */
+OFDM_API int ofdm_ctx_set_stream(ofdm_ctx* ctx, void* cuda_stream); /* cudaStream_t; NULL = own stream; (void*)1 = cudaStreamLegacy */
 OFDM_API int ofdm_sync(ofdm_ctx* ctx);
 OFDM_API int ofdm_precision(const ofdm_ctx* ctx);
 OFDM_API int ofdm_malloc(ofdm_ctx* ctx, void** dev, size_t bytes);

@@ -1,7 +1,292 @@
-// Fast path of the M1 RX chain (Nfft = 4096): placeholder until the radix-16 kernel lands.
-#include "common.cuh"
+// Fast path of the M1 RX chain: Nfft = 4096, N_carrier <= 1024, FP32.
+//
+// One persistent CTA of 256 threads walks whole streams.  Per OFDM symbol:
+//   global (CP skipped, 8-byte coalesced loads, 16 in flight per thread)
+//   -> radix-16 pass A in registers -> shared exchange -> pass B -> shared exchange
+//   -> pass C pruned to the 1,024 consumed bins (k3 < 4)   [OFDM_demodulator.m:5-8]
+//   -> symbol 0 only: pilot LS + edge extension + banded spline operator   [LS_CE.m:27-31]
+//   -> one-tap equalise, hard decision, frame-level DeScrambler + BER popcount
+//      [equalize_signal.m:6, get_payload.m:3, demapping.m:9-15, DeScrambler.m:8-13, BER_func.m:3]
+// Index algebra: n = 256 n1 + 16 n2 + n3, k = k1 + 16 k2 + 256 k3;
+//   W4096^{nk} = W16^{n1k1} * W4096^{(16n2+n3)k1} * W16^{n2k2} * W256^{n3k2} * W16^{n3k3}.
+// Only outputs k < 1024 are needed, so pass C evaluates 4 of its 16 outputs.
+#include "interp.cuh"
+
+#define FX_THREADS 256
+#define EX2_STRIDE_K2 272   // 16*17: pad so that the pass-C reads (stride 17) are bank-conflict free
+#define EX2_SIZE (16 * EX2_STRIDE_K2)
+#define SLOT_ZERO (-2147483647 - 1)
+
+const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
+uint32_t ofdm_reg_to_prev(const uint8_t* reg);
+
+__device__ __forceinline__ float2 ld_stream(const float2* p) {   // streaming load: do not allocate in L1
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
+    a0 = t0 + t2;
+    a2 = t0 - t2;
+    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
+    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+}
+#define C16_1 0.92387953251128674f
+#define S16_1 0.38268343236508977f
+#define RSQ2 0.70710678118654752f
+// v[4a+b] in  ->  X[c+4d] at v[4c+d]   (forward 16-point DFT, radix 4x4)
+__device__ __forceinline__ void fft16_steps12(float2* v) {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) fft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
+    // y_b[c] sits at v[4c+b]; multiply by W16^{bc}
+    float2 t;
+    t = v[5];  v[5]  = make_float2(t.x * C16_1 + t.y * S16_1, t.y * C16_1 - t.x * S16_1);       // W16^1
+    t = v[6];  v[6]  = make_float2((t.x + t.y) * RSQ2, (t.y - t.x) * RSQ2);                       // W16^2
+    t = v[7];  v[7]  = make_float2(t.x * S16_1 + t.y * C16_1, t.y * S16_1 - t.x * C16_1);       // W16^3
+    t = v[9];  v[9]  = make_float2((t.x + t.y) * RSQ2, (t.y - t.x) * RSQ2);                       // W16^2
+    t = v[10]; v[10] = make_float2(t.y, -t.x);                                                      // W16^4 = -i
+    t = v[11]; v[11] = make_float2((t.y - t.x) * RSQ2, -(t.x + t.y) * RSQ2);                      // W16^6
+    t = v[13]; v[13] = make_float2(t.x * S16_1 + t.y * C16_1, t.y * S16_1 - t.x * C16_1);       // W16^3
+    t = v[14]; v[14] = make_float2((t.y - t.x) * RSQ2, -(t.x + t.y) * RSQ2);                      // W16^6
+    t = v[15]; v[15] = make_float2(-t.x * C16_1 - t.y * S16_1, t.x * S16_1 - t.y * C16_1);      // W16^9
+}
+__device__ __forceinline__ void fft16(float2* v) {
+    fft16_steps12(v);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+struct Fast4096Params {
+    int Tg, S, SpF, Nc, Nd, Np, frame_words, frames, scramble, con_id;
+    uint32_t prev0;
+    const int32_t* slot;       // 1024 entries for carriers 0..1023 (data rank / -1-pilot / SLOT_ZERO)
+    const float2* pilots;      // Np (first symbol column)
+    const float2* tw4096;      // W4096^k
+    float inv_sqrt10;
+};
+
+// 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`):
+// table index = 4*Icode + Qcode, I levels {-3,-1,+3,+1} -> codes {0,1,2,3}, Q levels {+3,+1,-3,-1}.
+__device__ __forceinline__ int demap16(float x, float y, float two_a, float* margin) {
+    int ic = (x <= -two_a) ? 0 : (x <= 0.f) ? 1 : (x < two_a) ? 3 : 2;
+    int qc = (y >= two_a) ? 0 : (y >= 0.f) ? 1 : (y > -two_a) ? 3 : 2;
+    if (x != x || y != y) { ic = 0; qc = 0; }   // NaN never wins a '<': index 1 of the table
+    float ax = fabsf(x), ay = fabsf(y);
+    float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
+    *margin = 2.f * two_a * fminf(dx, dy);      // second-best minus best squared distance
+    return 4 * ic + qc;
+}
+
+template <bool QAM16>
+__global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
+                                                               int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
+                                                               float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
+                                                               int32_t* __restrict__ err_stream, float near_eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int red_i[32];
+    float2* ex1 = (float2*)smem_raw;            // 4096: idx = k1*256 + 16*n2 + n3
+    float2* ex2 = ex1 + 4096;                   // EX2_SIZE: idx = k2*272 + k1*17 + n3
+    float2* Hinv = ex2 + EX2_SIZE;              // 1024
+    float2* yk = Hinv + 1024;                   // n_knots
+    float2* dk = yk + plan.n_knots;             // n_knots
+    int32_t* slot_s = (int32_t*)(dk + plan.n_knots);   // 1024
+    uint32_t* raw = (uint32_t*)(slot_s + 1024); // frame_words
+    uint8_t* symidx = (uint8_t*)(raw + p.frame_words); // SpF*Nd
+    const int tid = threadIdx.x;
+    const int bps = con.bps;
+    for (int i = tid; i < 1024; i += FX_THREADS) slot_s[i] = p.slot[i];
+
+    // per-thread twiddles, resident for the whole kernel
+    float2 ta[16], tb[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) ta[k1] = p.tw4096[(tid * k1) & 4095];             // W4096^{t*k1}, t = 16 n2 + n3
+    {
+        const int n3 = tid & 15;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) tb[k2] = p.tw4096[(16 * n3 * k2) & 4095];     // W256^{n3*k2}
+    }
+    const int symlen = 4096 + p.Tg;
+    const int64_t stream_words = (int64_t)p.frame_words * p.frames;
+    const float two_a = 2.f * p.inv_sqrt10;
+    __syncthreads();
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        int errs = 0, nears = 0;
+        const float2* sbase = rx + b * (int64_t)p.S * symlen + p.Tg;
+        for (int s = 0; s < p.S; ++s) {
+            float2 v[16];
+            const float2* src = sbase + (int64_t)s * symlen + tid;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = ld_stream(src + 256 * n1);
+            // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, scatter by k1
+            fft16(v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int k1 = c + 4 * d;
+                    float2 x = v[4 * c + d];
+                    if (k1) x = cmul(x, ta[k1]);
+                    ex1[k1 * 256 + tid] = x;
+                }
+            __syncthreads();
+            // ---- pass B: thread (k1 = tid>>4, n3 = tid&15), DFT over n2
+            {
+                const float2* rp = ex1 + (tid >> 4) * 256 + (tid & 15);
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
+            }
+            fft16(v);
+            {
+                float2* wp = ex2 + (tid >> 4) * 17 + (tid & 15);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int k2 = c + 4 * d;
+                        float2 x = v[4 * c + d];
+                        if (k2) x = cmul(x, tb[k2]);
+                        wp[k2 * EX2_STRIDE_K2] = x;
+                    }
+            }
+            __syncthreads();
+            // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
+            {
+                const float2* rp = ex2 + (tid >> 4) * EX2_STRIDE_K2 + (tid & 15) * 17;
+#pragma unroll
+                for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3];
+            }
+            fft16_steps12(v);
+            float2 Y[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) Y[c] = (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);   // carrier tid + 256*c
+            // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
+            if (s == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int sl = slot_s[tid + 256 * c];
+                    if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cdiv(Y[c], p.pilots[pi]); }
+                }
+                __syncthreads();
+                plan_apply(plan, yk, dk, Hinv);   // Hinv temporarily holds H (nq = Nc entries)
+                __syncthreads();
+                for (int k = tid; k < p.Nc; k += FX_THREADS) {
+                    float2 h = Hinv[k];
+                    if (Hout) Hout[b * p.Nc + k] = h;
+                    float dd = h.x * h.x + h.y * h.y;
+                    Hinv[k] = make_float2(h.x / dd, -h.y / dd);
+                }
+                __syncthreads();
+            }
+            // ---- equalise + decide
+            const int sf = s % p.SpF;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int k = tid + 256 * c;
+                const int sl = slot_s[k];
+                if (sl >= 0) {
+                    float2 e = (k < p.Nc) ? cmul(Y[c], Hinv[k]) : make_float2(0.f, 0.f);
+                    float margin;
+                    int idx;
+                    if (QAM16) idx = demap16(e.x, e.y, two_a, &margin);
+                    else idx = nearest_idx(con, e.x, e.y, &margin);
+                    if (margin < near_eps) ++nears;
+                    symidx[sf * p.Nd + sl] = (uint8_t)idx;
+                }
+            }
+            // ---- frame complete: pack, DeScrambler, compare
+            if (sf == p.SpF - 1) {
+                __syncthreads();
+                const int f = s / p.SpF;
+                const int frame_bits = p.frame_words * 32;
+                for (int w = tid; w < p.frame_words; w += FX_THREADS) {
+                    uint32_t word = 0;
+                    if (QAM16) {
+                        const uint8_t* sp = symidx + 8 * w;    // 8 nibbles, each MSB-first inside LSB-first packing
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) word |= (__brev((uint32_t)sp[q]) >> 28) << (4 * q);
+                    } else {
+                        const int b0 = 32 * w, b1 = b0 + 32;
+                        for (int q = b0 / bps; q * bps < b1 && q * bps < frame_bits; ++q) {
+                            int idx = symidx[q];
+                            for (int i = 0; i < bps; ++i) {
+                                int pos = q * bps + i;
+                                if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                            }
+                        }
+                    }
+                    raw[w] = word;
+                }
+                __syncthreads();
+                const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
+                for (int w = tid; w < p.frame_words; w += FX_THREADS) {
+                    uint32_t cur = raw[w], o = cur;
+                    if (p.scramble) {
+                        uint32_t prev = w ? raw[w - 1] : p.prev0;
+                        o = cur ^ ((cur << 13) | (prev >> 19)) ^ ((cur << 14) | (prev >> 18));
+                    }
+                    if (txbits) errs += __popc(o ^ txbits[wbase + w]);
+                    if (outbits) outbits[wbase + w] = o;
+                }
+            }
+            __syncthreads();
+        }
+        errs = block_sum(errs, red_i);
+        nears = block_sum(nears, red_i);
+        if (tid == 0) {
+            if (counts) {
+                if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+                atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
+                if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+            }
+            if (err_stream) err_stream[b] = errs;
+        }
+    }
+}
+
 int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, const uint32_t* tx_bits, uint32_t* out_bits,
                            void* H, int64_t* counts, int32_t* err_stream, double near_eps, bool* handled) {
     *handled = false;
+    if (ctx->precision != OFDM_PREC_F32 || lp->Nfft != 4096 || lp->N_carrier > 1024 || lp->N_carrier < 2) return OFDM_OK;
+    ConstTable ct = host_constellation(lp->constellation);
+    if (ct.bps == 0 || lp->S <= 0 || lp->SpF <= 0 || lp->S % lp->SpF) return OFDM_OK;
+    const int frame_bits = lp->SpF * lp->Nd * ct.bps;
+    if (frame_bits % 32 != 0 || lp->Np < 2 || lp->Nd < 1) return OFDM_OK;       // unaligned frames take the generic kernel
+    if (getenv("OFDM_B200_NO_FAST")) return OFDM_OK;
+    std::vector<int32_t> slot(1024, SLOT_ZERO);
+    for (int i = 0; i < lp->Nd; ++i) { int c = lp->data_carriers_host[i]; if (c < 1 || c > lp->N_carrier) return OFDM_OK; slot[c - 1] = i; }
+    for (int i = 0; i < lp->Np; ++i) {
+        int c = lp->pilot_carriers_host[i];
+        if (c < 1 || c > lp->N_carrier || (i && c <= lp->pilot_carriers_host[i - 1])) return OFDM_OK;
+        slot[c - 1] = -1 - i;
+    }
+    const InterpPlan* pl = ctx_plan(ctx, lp->pilot_carriers_host, lp->Np, lp->N_carrier, nullptr, lp->N_carrier, OFDM_INTERP_SPLINE);
+    REQUIRE(ctx, pl != nullptr, "plan construction failed");
+    Fast4096Params p;
+    p.Tg = lp->Tg; p.S = lp->S; p.SpF = lp->SpF; p.Nc = lp->N_carrier; p.Nd = lp->Nd; p.Np = lp->Np;
+    p.frame_words = frame_bits / 32; p.frames = lp->S / lp->SpF; p.scramble = lp->scramble; p.con_id = lp->constellation;
+    p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
+    p.slot = (const int32_t*)ctx_blob(ctx, slot.data(), sizeof(int32_t) * 1024);
+    p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, lp->Np);
+    p.tw4096 = (const float2*)ctx_twiddles(ctx, 4096);
+    p.inv_sqrt10 = (float)ct.re[12];   // +1/sqrt(10) with the table's own normalisation
+    REQUIRE(ctx, p.slot && p.pilots && p.tw4096, "device upload failed");
+    size_t smem = sizeof(float2) * (4096 + EX2_SIZE + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 + sizeof(uint32_t) * p.frame_words +
+                  (size_t)lp->SpF * lp->Nd + 16;
+    if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
+    const bool q16 = lp->constellation == OFDM_16QAM;
+    auto k16 = rx4096_kernel<true>;
+    auto kgen = rx4096_kernel<false>;
+    CUDA_TRY(ctx, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kgen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
+    DevConst<float> con = make_devconst<float>(lp->constellation);
+    PlanDev<float> pd = plan_dev<float>(pl);
+    if (q16) k16<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream, (float)near_eps);
+    else kgen<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream, (float)near_eps);
+    LAUNCH_CHECK(ctx);
+    *handled = true;
     return OFDM_OK;
 }

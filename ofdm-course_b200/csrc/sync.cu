@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __res
     double* Sa = Sim + (AC_TILE + W);
     double* Sb = Sa + (AC_TILE + W);
     __shared__ double wtot[4][AC_THREADS / 32];
+    __shared__ double tot[4][AC_THREADS];
     const cx<T>* r = rx + b * L;
     const int tid = threadIdx.x;
     for (int i = tid; i < M; i += AC_THREADS) {
@@ -48,15 +49,17 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __res
         t2 += Sa[i]; Sa[i] = t2;
         t3 += Sb[i]; Sb[i] = t3;
     }
-    double v[4] = {t0, t1, t2, t3};
+    // Offsets of the chunks.  They must come from ONE fixed summation order: a run of exactly-zero
+    // samples (STO zero fill) then leaves the prefix bit-identical on both sides of a window, so the
+    // window sums are exactly 0 and 0/0 gives the reference's NaN (`AutoCorrFunction.m:6`).
     const int lane = tid & 31, w = tid >> 5;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double x = v[q];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { double y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-        if (lane == 31) wtot[q][w] = x;
-        v[q] = x;  // inclusive over the warp
+    tot[0][tid] = t0; tot[1][tid] = t1; tot[2][tid] = t2; tot[3][tid] = t3;
+    __syncthreads();
+    if (tid < 4 * (AC_THREADS / 32)) {            // one thread per (quantity, warp): sequential lane scan
+        const int q = tid & 3, ww = tid >> 2;
+        double run = 0;
+        for (int l = 0; l < 32; ++l) { double x = tot[q][ww * 32 + l]; tot[q][ww * 32 + l] = run; run += x; }
+        wtot[q][ww] = run;
     }
     __syncthreads();
     double off[4];
@@ -64,8 +67,7 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __res
     for (int q = 0; q < 4; ++q) {
         double base = 0;
         for (int k = 0; k < w; ++k) base += wtot[q][k];
-        double own = (q == 0 ? t0 : q == 1 ? t1 : q == 2 ? t2 : t3);
-        off[q] = base + v[q] - own;   // exclusive prefix of this thread's chunk
+        off[q] = base + tot[q][tid];
     }
     for (int i = lo; i < hi; ++i) { Sre[i] += off[0]; Sim[i] += off[1]; Sa[i] += off[2]; Sb[i] += off[3]; }
     __syncthreads();

@@ -73,7 +73,7 @@ class Context:
         self.rdtype = torch.float64 if self.f64 else torch.float32
         with torch.cuda.device(self.device):
             self._stream = torch.cuda.current_stream()
-            self._chk(self.lib.ofdm_ctx_set_stream(self.h, C.c_void_p(self._stream.cuda_stream)))
+            self._chk(self.lib.ofdm_ctx_set_stream(self.h, C.c_void_p(self._stream.cuda_stream or 1)))  # 0 -> cudaStreamLegacy
 
     def close(self):
         if getattr(self, "h", None):
@@ -94,7 +94,7 @@ class Context:
     def use_current_stream(self):
         s = torch.cuda.current_stream(self.device)
         self._stream = s
-        self._chk(self.lib.ofdm_ctx_set_stream(self.h, C.c_void_p(s.cuda_stream)))
+        self._chk(self.lib.ofdm_ctx_set_stream(self.h, C.c_void_p(s.cuda_stream or 1)))
 
     def sync(self):
         self._chk(self.lib.ofdm_sync(self.h))

@@ -77,9 +77,13 @@ def params_task4(percent=15, scale=4.0 / 3.0, alternate=True, Constellation="16Q
     return p
 
 
-def scramble_frames(p: LinkParams, bits, descramble=False):
-    """Per-frame register reset (`Task 4/Main_model_Task_4.m:43-58`, `:350-364`)."""
-    fn = F.DeScrambler if descramble else F.Scrambler
+def scramble_frames(p: LinkParams, bits, descramble=False, fast=False):
+    """Per-frame register reset (`Task 4/Main_model_Task_4.m:43-58`, `:350-364`).  ``fast`` selects the
+    vectorised (bit-identical) forms, used only where the oracle is timed as the CPU baseline."""
+    if fast:
+        fn = F.DeScrambler_fast if descramble else F.Scrambler_fast
+    else:
+        fn = F.DeScrambler if descramble else F.Scrambler
     L = p.frame_bits
     out = np.empty(p.stream_bits, dtype=np.uint8)
     for i in range(p.Amount_OFDM_Frames):
@@ -87,11 +91,11 @@ def scramble_frames(p: LinkParams, bits, descramble=False):
     return out
 
 
-def tx_chain(p: LinkParams, input_bits, scramble=True):
+def tx_chain(p: LinkParams, input_bits, scramble=True, fast=False):
     """bits -> Scrambler -> mapping -> OFDM_map_carriers -> OFDM_modulator -> serial stream
     (`Task 5/Main_model_Task_5.m:53-85`).  Returns (stream, grid, sc_bits)."""
     bits = np.asarray(input_bits).ravel()
-    sc = scramble_frames(p, bits) if scramble else bits.astype(np.uint8)
+    sc = scramble_frames(p, bits, fast=fast) if scramble else bits.astype(np.uint8)
     iq, pad = F.mapping(sc, p.Constellation)
     grid = F.OFDM_map_carriers(iq, p.N_symb, p.Nfft, p.dataCarriers, p.pilotCarriers, p.pilotValues)
     tx = F.OFDM_modulator(grid, p.T_Guard)
@@ -109,7 +113,7 @@ def channel_task5(p: LinkParams, tx, SNR_dB, taps, normals=None, rng=None):
     return rx
 
 
-def rx_chain_task5(p: LinkParams, rx_stream, input_bits, descramble=True, method="LS", h_true=None, SNR_dB=None):
+def rx_chain_task5(p: LinkParams, rx_stream, input_bits, descramble=True, method="LS", h_true=None, SNR_dB=None, fast=False):
     """M1 chain: OFDM_demodulator -> LS_CE -> equalize_signal -> get_payload -> demapping ->
     DeScrambler -> BER_func (`Task 5/Task5_part2.m:169-174,269-303`, per-frame descrambler
     reset as `Task 5/Main_model_Task_5.m:262-271`).  Returns dict."""
@@ -125,7 +129,7 @@ def rx_chain_task5(p: LinkParams, rx_stream, input_bits, descramble=True, method
     eq = F.equalize_signal(Y, H, p.N_carrier)
     rx_iq = F.get_payload(eq, p.dataCarriers).ravel(order="F")
     out_bits = F.demapping(-1, rx_iq, p.Constellation)
-    dsc = scramble_frames(p, out_bits, descramble=True) if descramble else out_bits
+    dsc = scramble_frames(p, out_bits, descramble=True, fast=fast) if descramble else out_bits
     tx_bits = np.asarray(input_bits).ravel()
     n_err = int(np.sum(tx_bits != dsc))
     return {"Y": Y, "H": H, "eq": eq, "rx_iq": rx_iq, "bits": dsc, "raw_bits": out_bits,

@@ -23,6 +23,7 @@ __all__ = [
     "interpolate", "equalize_signal", "OMP_estimate", "MP_estimate", "BER_func", "MER_func",
     "interp1_spline", "sensing_matrix_dft", "pilot_layout_percent", "pilot_layout_comb",
     "calculatePAPR", "calculate_window_PAPR", "calculateCCDF", "DEFAULT_REGISTER",
+    "Scrambler_fast", "DeScrambler_fast",
 ]
 
 #: initial scrambler register used by every script (`Task 4/Main_model_Task_4.m:43`)
@@ -59,6 +60,41 @@ def DeScrambler(Register, sequence):
         out[i] = (reg[12] ^ reg[13]) ^ feedback                 # :9-10
         reg = [feedback] + reg[:-1]                             # :12-13
     return out, np.array(reg, dtype=np.uint8)
+
+
+def DeScrambler_fast(Register, sequence):
+    """Vectorised DeScrambler (same result as the loop above; used where the oracle is *timed* so the
+    CPU baseline is not dominated by a Python per-bit loop): out[i] = in[i] ^ in[i-13] ^ in[i-14]
+    with pre-history in[-m] = Register(m)."""
+    reg = np.asarray(Register).ravel().astype(np.uint8) & 1
+    seq = np.asarray(sequence).ravel().astype(np.uint8) & 1
+    ext = np.concatenate([reg[::-1], seq])                      # ext[15 + i] = in[i], ext[15 - m] = Register(m)
+    out = seq ^ ext[15 - 13: 15 - 13 + seq.size] ^ ext[15 - 14: 15 - 14 + seq.size]
+    tail = np.concatenate([reg[::-1], seq])[::-1][:15]
+    return out, tail.astype(np.uint8)
+
+
+def Scrambler_fast(Register, sequence):
+    """Vectorised Scrambler via the GF(2) identity 1/(1+p) = prod_j (1 + p^(2^j)), p = x^13 + x^14
+    (SURVEY KAT 2); same result as the loop above."""
+    reg = np.asarray(Register).ravel().astype(np.uint8) & 1
+    t = (np.asarray(sequence).ravel().astype(np.uint8) & 1).copy()
+    L = t.size
+    for i in range(min(14, L)):                                  # fold the register pre-history into the input
+        a = reg[12 - i] if 12 - i >= 0 else 0
+        b = reg[13 - i] if 13 - i >= 0 else 0
+        t[i] ^= a ^ b
+    j = 0
+    while (13 << j) < L:
+        s13, s14 = 13 << j, 14 << j
+        u = t.copy()
+        u[s13:] ^= t[:L - s13]
+        if s14 < L:
+            u[s14:] ^= t[:L - s14]
+        t = u
+        j += 1
+    tail = np.concatenate([reg[::-1], t])[::-1][:15]
+    return t, tail.astype(np.uint8)
 
 
 # --------------------------------------------------------------------------- a3

@@ -82,7 +82,7 @@ def test_constellation_mapping_demapping(G, name):
             assert pad == pad_ref and np.max(np.abs(iq - iq_ref)) < tol
             assert np.array_equal(G.demapping(pad, iq, name, precision=prec), bits)
     # noisy points: decisions equal the oracle's except within epsilon of a boundary
-    iq = iq_ref[:300] + 0.3 * crandn(rng, 300)
+    iq = d_ref[rng.integers(0, d_ref.size, 300)] + 0.3 * crandn(rng, 300)
     ref = O.demapping(-1, iq, name)
     got = G.demapping(-1, iq, name, precision="f64")
     assert np.array_equal(got, ref)

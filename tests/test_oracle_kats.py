@@ -264,3 +264,16 @@ def test_payload_reader_matches_survey_stats():
         pytest.skip("reference fixture only exists in the build container")
     bits = C.read_payload_bits(path, 129600)
     assert bits.size == 129600 and abs(bits.mean() - 0.337) < 0.005
+
+
+@pytest.mark.parametrize("L", [1, 5, 13, 14, 15, 16, 100, 6640])
+def test_fast_scrambler_forms_equal_the_loops(L):
+    rng = np.random.default_rng(L)
+    x = rng.integers(0, 2, L).astype(np.uint8)
+    for reg in (O.DEFAULT_REGISTER, rng.integers(0, 2, 15).astype(np.uint8)):
+        a, ra = O.Scrambler(reg, x)
+        b, rb = O.Scrambler_fast(reg, x)
+        assert np.array_equal(a, b) and np.array_equal(ra, rb)
+        c, rc = O.DeScrambler(reg, a)
+        d, rd = O.DeScrambler_fast(reg, a)
+        assert np.array_equal(c, d) and np.array_equal(rc, rd) and np.array_equal(c, x)
