@@ -287,7 +287,7 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU per step (M1: 65,536 = 917,504 symbols)")
     ap.add_argument("--e2e-streams", type=int, default=4096)
     ap.add_argument("--e2e-chunk", type=int, default=512)
-    ap.add_argument("--ref-streams", type=int, default=24, help="streams per host process in the CPU sample")
+    ap.add_argument("--ref-streams", type=int, default=600, help="streams per host process in the CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
