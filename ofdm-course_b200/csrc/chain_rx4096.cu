@@ -13,8 +13,6 @@
 #include "interp.cuh"
 
 #define FX_THREADS 256
-#define EX2_STRIDE_K2 272   // 16*17: pad so that the pass-C reads (stride 17) are bank-conflict free
-#define EX2_SIZE (16 * EX2_STRIDE_K2)
 #define SLOT_ZERO (-2147483647 - 1)
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
@@ -69,26 +67,60 @@ struct Fast4096Params {
 
 // 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`):
 // table index = 4*Icode + Qcode, I levels {-3,-1,+3,+1} -> codes {0,1,2,3}, Q levels {+3,+1,-3,-1}.
+template <bool NEAR>
 __device__ __forceinline__ int demap16(float x, float y, float two_a, float* margin) {
     int ic = (x <= -two_a) ? 0 : (x <= 0.f) ? 1 : (x < two_a) ? 3 : 2;
     int qc = (y >= two_a) ? 0 : (y >= 0.f) ? 1 : (y > -two_a) ? 3 : 2;
     if (x != x || y != y) { ic = 0; qc = 0; }   // NaN never wins a '<': index 1 of the table
-    float ax = fabsf(x), ay = fabsf(y);
-    float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
-    *margin = 2.f * two_a * fminf(dx, dy);      // second-best minus best squared distance
+    if (NEAR) {
+        float ax = fabsf(x), ay = fabsf(y);
+        float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
+        *margin = 2.f * two_a * fminf(dx, dy);  // second-best minus best squared distance
+    }
     return 4 * ic + qc;
 }
 
-template <bool QAM16>
+// ---- mbarrier / bulk-copy (TMA) helpers --------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Work item q of this CTA = (stream blockIdx.x + (q / S) * gridDim.x, symbol q % S).  Symbols are
+// prefetched two items ahead into a two-buffer ring by one elected thread; all three FFT passes run
+// in place in the buffer the symbol landed in:
+//   pass A  x[256 n1 + t]            -> same places, index k1 replaces n1          (thread-private)
+//   pass B  [256 k1 + 16 n2 + n3]    -> [256 k1 + 16 k2 + (n3 ^ k1)]                (XOR swizzle)
+//   pass C  reads 16 consecutive (swizzled) n3 per (k1,k2): conflict-free because of the swizzle.
+template <bool QAM16, bool NEAR>
 __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
                                                                int32_t* __restrict__ err_stream, float near_eps) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int red_i[32];
-    float2* ex1 = (float2*)smem_raw;            // 4096: idx = k1*256 + 16*n2 + n3
-    float2* ex2 = ex1 + 4096;                   // EX2_SIZE: idx = k2*272 + k1*17 + n3
-    float2* Hinv = ex2 + EX2_SIZE;              // 1024
+    __shared__ __align__(8) uint64_t bars[2];
+    float2* xb0 = (float2*)smem_raw;            // two 4096-sample symbol buffers (ring)
+    float2* Hinv = xb0 + 2 * 4096;              // 1024
     float2* yk = Hinv + 1024;                   // n_knots
     float2* dk = yk + plan.n_knots;             // n_knots
     int32_t* slot_s = (int32_t*)(dk + plan.n_knots);   // 1024
@@ -110,138 +142,163 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     const int symlen = 4096 + p.Tg;
     const int64_t stream_words = (int64_t)p.frame_words * p.frames;
     const float two_a = 2.f * p.inv_sqrt10;
+    const int64_t my_streams = (B - blockIdx.x + gridDim.x - 1) / gridDim.x;
+    const int64_t n_items = my_streams * p.S;
+    auto item_src = [&](int64_t q) -> const float2* {
+        const int64_t b = blockIdx.x + (q / p.S) * (int64_t)gridDim.x;
+        return rx + (b * p.S + (q % p.S)) * (int64_t)symlen + p.Tg;
+    };
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-        int errs = 0, nears = 0;
-        const float2* sbase = rx + b * (int64_t)p.S * symlen + p.Tg;
-        for (int s = 0; s < p.S; ++s) {
-            float2 v[16];
-            const float2* src = sbase + (int64_t)s * symlen + tid;
+    if (tid == 0) {
+        for (int i = 0; i < 2 && i < n_items; ++i) {
+            mbar_expect_tx(&bars[i], 32768u);
+            bulk_g2s(xb0 + i * 4096, item_src(i), 32768u, &bars[i]);
+        }
+    }
+    int errs = 0, nears = 0;
+    for (int64_t q = 0; q < n_items; ++q) {
+        const int cur = (int)(q & 1);
+        const int s = (int)(q % p.S);
+        const int64_t b = blockIdx.x + (q / p.S) * (int64_t)gridDim.x;
+        float2* X = xb0 + cur * 4096;
+        float2 v[16];
+        mbar_wait(&bars[cur], (uint32_t)((q >> 1) & 1));
+        // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, in place
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) v[n1] = ld_stream(src + 256 * n1);
-            // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, scatter by k1
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
+        fft16(v);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int k1 = c + 4 * d;
+                float2 x = v[4 * c + d];
+                if (k1) x = cmul(x, ta[k1]);
+                X[k1 * 256 + tid] = x;
+            }
+        __syncthreads();
+        // ---- pass B: thread (k1 = tid>>4, n3 = tid&15), DFT over n2, swizzled write-back
+        {
+            float2* rp = X + (tid >> 4) * 256 + (tid & 15);
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
+            __syncthreads();                       // every read precedes the swizzled writes
             fft16(v);
+            float2* wp = X + (tid >> 4) * 256 + ((tid & 15) ^ (tid >> 4));
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    const int k1 = c + 4 * d;
+                    const int k2 = c + 4 * d;
                     float2 x = v[4 * c + d];
-                    if (k1) x = cmul(x, ta[k1]);
-                    ex1[k1 * 256 + tid] = x;
+                    if (k2) x = cmul(x, tb[k2]);
+                    wp[16 * k2] = x;
                 }
-            __syncthreads();
-            // ---- pass B: thread (k1 = tid>>4, n3 = tid&15), DFT over n2
-            {
-                const float2* rp = ex1 + (tid >> 4) * 256 + (tid & 15);
+        }
+        __syncthreads();
+        // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
+        {
+            const int k1 = tid & 15;
+            const float2* rp = X + k1 * 256 + (tid >> 4) * 16;
 #pragma unroll
-                for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
-            }
-            fft16(v);
-            {
-                float2* wp = ex2 + (tid >> 4) * 17 + (tid & 15);
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3 ^ k1];
+        }
+        __syncthreads();                           // buffer `cur` is free: refill it with item q+2
+        if (tid == 0 && q + 2 < n_items) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[cur], 32768u);
+            bulk_g2s(X, item_src(q + 2), 32768u, &bars[cur]);
+        }
+        fft16_steps12(v);
+        float2 Y[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int d = 0; d < 4; ++d) {
-                        const int k2 = c + 4 * d;
-                        float2 x = v[4 * c + d];
-                        if (k2) x = cmul(x, tb[k2]);
-                        wp[k2 * EX2_STRIDE_K2] = x;
-                    }
-            }
-            __syncthreads();
-            // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
-            {
-                const float2* rp = ex2 + (tid >> 4) * EX2_STRIDE_K2 + (tid & 15) * 17;
-#pragma unroll
-                for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3];
-            }
-            fft16_steps12(v);
-            float2 Y[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Y[c] = (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);   // carrier tid + 256*c
-            // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
-            if (s == 0) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int sl = slot_s[tid + 256 * c];
-                    if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cdiv(Y[c], p.pilots[pi]); }
-                }
-                __syncthreads();
-                plan_apply(plan, yk, dk, Hinv);   // Hinv temporarily holds H (nq = Nc entries)
-                __syncthreads();
-                for (int k = tid; k < p.Nc; k += FX_THREADS) {
-                    float2 h = Hinv[k];
-                    if (Hout) Hout[b * p.Nc + k] = h;
-                    float dd = h.x * h.x + h.y * h.y;
-                    Hinv[k] = make_float2(h.x / dd, -h.y / dd);
-                }
-                __syncthreads();
-            }
-            // ---- equalise + decide
-            const int sf = s % p.SpF;
+        for (int c = 0; c < 4; ++c) Y[c] = (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);   // carrier tid + 256*c
+        // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
+        if (s == 0) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int k = tid + 256 * c;
-                const int sl = slot_s[k];
-                if (sl >= 0) {
-                    float2 e = (k < p.Nc) ? cmul(Y[c], Hinv[k]) : make_float2(0.f, 0.f);
-                    float margin;
-                    int idx;
-                    if (QAM16) idx = demap16(e.x, e.y, two_a, &margin);
-                    else idx = nearest_idx(con, e.x, e.y, &margin);
-                    if (margin < near_eps) ++nears;
-                    symidx[sf * p.Nd + sl] = (uint8_t)idx;
-                }
+                const int sl = slot_s[tid + 256 * c];
+                if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cdiv(Y[c], p.pilots[pi]); }
             }
-            // ---- frame complete: pack, DeScrambler, compare
-            if (sf == p.SpF - 1) {
-                __syncthreads();
-                const int f = s / p.SpF;
-                const int frame_bits = p.frame_words * 32;
-                for (int w = tid; w < p.frame_words; w += FX_THREADS) {
-                    uint32_t word = 0;
-                    if (QAM16) {
-                        const uint8_t* sp = symidx + 8 * w;    // 8 nibbles, each MSB-first inside LSB-first packing
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) word |= (__brev((uint32_t)sp[q]) >> 28) << (4 * q);
-                    } else {
-                        const int b0 = 32 * w, b1 = b0 + 32;
-                        for (int q = b0 / bps; q * bps < b1 && q * bps < frame_bits; ++q) {
-                            int idx = symidx[q];
-                            for (int i = 0; i < bps; ++i) {
-                                int pos = q * bps + i;
-                                if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
-                            }
-                        }
-                    }
-                    raw[w] = word;
-                }
-                __syncthreads();
-                const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
-                for (int w = tid; w < p.frame_words; w += FX_THREADS) {
-                    uint32_t cur = raw[w], o = cur;
-                    if (p.scramble) {
-                        uint32_t prev = w ? raw[w - 1] : p.prev0;
-                        o = cur ^ ((cur << 13) | (prev >> 19)) ^ ((cur << 14) | (prev >> 18));
-                    }
-                    if (txbits) errs += __popc(o ^ txbits[wbase + w]);
-                    if (outbits) outbits[wbase + w] = o;
-                }
+            __syncthreads();
+            plan_apply(plan, yk, dk, Hinv);   // Hinv temporarily holds H (nq = Nc entries)
+            __syncthreads();
+            for (int k = tid; k < p.Nc; k += FX_THREADS) {
+                float2 h = Hinv[k];
+                if (Hout) Hout[b * p.Nc + k] = h;
+                float dd = h.x * h.x + h.y * h.y;
+                Hinv[k] = make_float2(h.x / dd, -h.y / dd);
             }
             __syncthreads();
         }
-        errs = block_sum(errs, red_i);
-        nears = block_sum(nears, red_i);
-        if (tid == 0) {
-            if (counts) {
-                if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
-                atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
-                if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+        // ---- equalise + decide
+        const int sf = s % p.SpF;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int k = tid + 256 * c;
+            const int sl = slot_s[k];
+            if (sl >= 0) {
+                float2 e = (k < p.Nc) ? cmul(Y[c], Hinv[k]) : make_float2(0.f, 0.f);
+                float margin = 1.f;
+                int idx;
+                if (QAM16) idx = demap16<NEAR>(e.x, e.y, two_a, &margin);
+                else idx = nearest_idx(con, e.x, e.y, &margin);
+                if (NEAR && margin < near_eps) ++nears;
+                symidx[sf * p.Nd + sl] = (uint8_t)idx;
             }
-            if (err_stream) err_stream[b] = errs;
+        }
+        // ---- frame complete: pack, DeScrambler, compare
+        if (sf == p.SpF - 1) {
+            __syncthreads();
+            const int f = s / p.SpF;
+            const int frame_bits = p.frame_words * 32;
+            for (int w = tid; w < p.frame_words; w += FX_THREADS) {
+                uint32_t word = 0;
+                if (QAM16) {
+                    const uint8_t* sp = symidx + 8 * w;    // 8 nibbles, each MSB-first inside LSB-first packing
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) word |= (__brev((uint32_t)sp[j]) >> 28) << (4 * j);
+                } else {
+                    const int b0 = 32 * w, b1 = b0 + 32;
+                    for (int j = b0 / bps; j * bps < b1 && j * bps < frame_bits; ++j) {
+                        int idx = symidx[j];
+                        for (int i = 0; i < bps; ++i) {
+                            int pos = j * bps + i;
+                            if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                        }
+                    }
+                }
+                raw[w] = word;
+            }
+            __syncthreads();
+            const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
+            for (int w = tid; w < p.frame_words; w += FX_THREADS) {
+                uint32_t cw = raw[w], o = cw;
+                if (p.scramble) {
+                    uint32_t prev = w ? raw[w - 1] : p.prev0;
+                    o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+                }
+                if (txbits) errs += __popc(o ^ txbits[wbase + w]);
+                if (outbits) outbits[wbase + w] = o;
+            }
+        }
+        if (s == p.S - 1) {   // stream complete
+            errs = block_sum(errs, red_i);
+            if (NEAR) nears = block_sum(nears, red_i);
+            if (tid == 0) {
+                if (counts) {
+                    if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+                    atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
+                    if (NEAR && nears) atomicAdd(&counts[2], (unsigned long long)nears);
+                }
+                if (err_stream) err_stream[b] = errs;
+            }
+            errs = 0; nears = 0;
         }
     }
 }
@@ -273,19 +330,22 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     p.tw4096 = (const float2*)ctx_twiddles(ctx, 4096);
     p.inv_sqrt10 = (float)ct.re[12];   // +1/sqrt(10) with the table's own normalisation
     REQUIRE(ctx, p.slot && p.pilots && p.tw4096, "device upload failed");
-    size_t smem = sizeof(float2) * (4096 + EX2_SIZE + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 + sizeof(uint32_t) * p.frame_words +
+    if (lp->Tg & 1) return OFDM_OK;          // bulk copies need 16-byte aligned symbol starts
+    if (((uintptr_t)rx) & 15) return OFDM_OK;
+    size_t smem = sizeof(float2) * (2 * 4096 + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 + sizeof(uint32_t) * p.frame_words +
                   (size_t)lp->SpF * lp->Nd + 16;
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
     const bool q16 = lp->constellation == OFDM_16QAM;
-    auto k16 = rx4096_kernel<true>;
-    auto kgen = rx4096_kernel<false>;
-    CUDA_TRY(ctx, cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(ctx, cudaFuncSetAttribute(kgen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool near = near_eps > 0.0;
+    void (*kern)(Fast4096Params, PlanDev<float>, DevConst<float>, const float2*, int64_t, const uint32_t*, uint32_t*, float2*, unsigned long long*,
+                 int32_t*, float) = q16 ? (near ? rx4096_kernel<true, true> : rx4096_kernel<true, false>)
+                                        : (near ? rx4096_kernel<false, true> : rx4096_kernel<false, false>);
+    CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
     DevConst<float> con = make_devconst<float>(lp->constellation);
     PlanDev<float> pd = plan_dev<float>(pl);
-    if (q16) k16<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream, (float)near_eps);
-    else kgen<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream, (float)near_eps);
+    kern<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream,
+                                                  (float)near_eps);
     LAUNCH_CHECK(ctx);
     *handled = true;
     return OFDM_OK;
