@@ -24,12 +24,18 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {   // streaming lo
     return r;
 }
 
+// Packed FP32x2 arithmetic (FADD2 / FFMA2, new on sm_100): one issue slot per complex add.  Measured on
+// B200 (tools/ubench_fp32x2.cu): FADD2 127, FFMA2 117, scalar FADD 117, scalar 3-register FFMA 71
+// results/clk/SM -- the packed forms halve the issue slots of the butterflies.
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 __device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    float2 t0 = a0 + a2, t1 = a0 - a2, t2 = a1 + a3, t3 = a1 - a3;
-    a0 = t0 + t2;
-    a2 = t0 - t2;
-    a1 = make_float2(t1.x + t3.y, t1.y - t3.x);
-    a3 = make_float2(t1.x - t3.y, t1.y + t3.x);
+    const float2 t0 = add2(a0, a2), t1 = sub2(a0, a2), t2 = add2(a1, a3);
+    const float2 t3s = make_float2(a1.y - a3.y, a1.x - a3.x);          // (a1 - a3) with the halves swapped
+    a0 = add2(t0, t2);
+    a2 = sub2(t0, t2);
+    a1 = __ffma2_rn(t3s, make_float2(1.f, -1.f), t1);                   // t1 + (-i)(a1 - a3)
+    a3 = __ffma2_rn(t3s, make_float2(-1.f, 1.f), t1);                   // t1 - (-i)(a1 - a3)
 }
 #define C16_1 0.92387953251128674f
 #define S16_1 0.38268343236508977f
@@ -65,19 +71,21 @@ struct Fast4096Params {
     float inv_sqrt10;
 };
 
-// 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`):
-// table index = 4*Icode + Qcode, I levels {-3,-1,+3,+1} -> codes {0,1,2,3}, Q levels {+3,+1,-3,-1}.
+// 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`).
+// Table index = 8*(x>0) + 4*(|x|<2a) + 2*(y<0) + (|y|<2a): I levels {-3,-1,+3,+1} -> codes {00,01,10,11},
+// Q levels {+3,+1,-3,-1} -> {00,01,10,11}; ties (x = 0, |x| = 2a, ...) fall to the lower table index
+// exactly as `min` does, and a NaN never wins a '<' so it decodes to index 1 (bits 0000).
+// Returned value is the index bit-reversed (MSB-first symbol bits inside LSB-first packing).
 template <bool NEAR>
-__device__ __forceinline__ int demap16(float x, float y, float two_a, float* margin) {
-    int ic = (x <= -two_a) ? 0 : (x <= 0.f) ? 1 : (x < two_a) ? 3 : 2;
-    int qc = (y >= two_a) ? 0 : (y >= 0.f) ? 1 : (y > -two_a) ? 3 : 2;
-    if (x != x || y != y) { ic = 0; qc = 0; }   // NaN never wins a '<': index 1 of the table
+__device__ __forceinline__ uint32_t demap16_nib(float x, float y, float two_a, float* margin) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    uint32_t nib = (x > 0.f ? 1u : 0u) | (ax < two_a ? 2u : 0u) | (y < 0.f ? 4u : 0u) | (ay < two_a ? 8u : 0u);
+    if (!(ax <= CUDART_INF_F) || !(ay <= CUDART_INF_F)) nib = 0u;       // NaN in either part
     if (NEAR) {
-        float ax = fabsf(x), ay = fabsf(y);
         float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
         *margin = 2.f * two_a * fminf(dx, dy);  // second-best minus best squared distance
     }
-    return 4 * ic + qc;
+    return nib;
 }
 
 // ---- mbarrier / bulk-copy (TMA) helpers --------------------------------------------------------
@@ -124,8 +132,8 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     float2* yk = Hinv + 1024;                   // n_knots
     float2* dk = yk + plan.n_knots;             // n_knots
     int32_t* slot_s = (int32_t*)(dk + plan.n_knots);   // 1024
-    uint32_t* raw = (uint32_t*)(slot_s + 1024); // frame_words
-    uint8_t* symidx = (uint8_t*)(raw + p.frame_words); // SpF*Nd
+    uint8_t* symidx = (uint8_t*)(slot_s + 1024);        // SpF*Nd decisions of the current frame (8-byte aligned)
+    uint32_t* raw = (uint32_t*)(symidx + ((p.SpF * p.Nd + 7) & ~7));   // frame_words
     const int tid = threadIdx.x;
     const int bps = con.bps;
     for (int i = tid; i < 1024; i += FX_THREADS) slot_s[i] = p.slot[i];
@@ -144,30 +152,46 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     const float two_a = 2.f * p.inv_sqrt10;
     const int64_t my_streams = (B - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t n_items = my_streams * p.S;
-    auto item_src = [&](int64_t q) -> const float2* {
-        const int64_t b = blockIdx.x + (q / p.S) * (int64_t)gridDim.x;
-        return rx + (b * p.S + (q % p.S)) * (int64_t)symlen + p.Tg;
-    };
+    const int64_t stream_stride = (int64_t)p.S * symlen;                 // samples per stream
+    const float2* rx0 = rx + (int64_t)blockIdx.x * stream_stride + p.Tg; // first symbol of this CTA's first stream
+    // per-thread carrier roles (fixed for the whole kernel): data rank or 0xFFFF, two per register
+    uint32_t role01, role23;
+    {
+        uint32_t r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { int sl = p.slot[tid + 256 * c]; r[c] = (sl >= 0 && tid + 256 * c < p.Nc) ? (uint32_t)sl : 0xFFFFu; }
+        role01 = r[0] | (r[1] << 16); role23 = r[2] | (r[3] << 16);
+    }
     if (tid == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // prefetch cursor (used by thread 0 only): item q+2 -> (stream offset, symbol)
+    const float2* pf_ptr = rx0;
+    int pf_s = 0;
+    auto pf_advance = [&]() {
+        if (++pf_s == p.S) { pf_s = 0; pf_ptr += (int64_t)gridDim.x * stream_stride - (int64_t)(p.S - 1) * symlen; }
+        else pf_ptr += symlen;
+    };
     if (tid == 0) {
         for (int i = 0; i < 2 && i < n_items; ++i) {
             mbar_expect_tx(&bars[i], 32768u);
-            bulk_g2s(xb0 + i * 4096, item_src(i), 32768u, &bars[i]);
+            bulk_g2s(xb0 + i * 4096, pf_ptr, 32768u, &bars[i]);
+            pf_advance();
         }
     }
     int errs = 0, nears = 0;
+    int s = 0, sf = 0, f = 0;
+    int64_t b = blockIdx.x;
+    uint32_t parity = 0;
     for (int64_t q = 0; q < n_items; ++q) {
         const int cur = (int)(q & 1);
-        const int s = (int)(q % p.S);
-        const int64_t b = blockIdx.x + (q / p.S) * (int64_t)gridDim.x;
         float2* X = xb0 + cur * 4096;
         float2 v[16];
-        mbar_wait(&bars[cur], (uint32_t)((q >> 1) & 1));
+        mbar_wait(&bars[cur], parity);
+        parity ^= (uint32_t)cur;                   // flips after both buffers have been used once
         // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, in place
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
@@ -212,12 +236,13 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         if (tid == 0 && q + 2 < n_items) {
             fence_proxy_async();
             mbar_expect_tx(&bars[cur], 32768u);
-            bulk_g2s(X, item_src(q + 2), 32768u, &bars[cur]);
+            bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
+            pf_advance();
         }
         fft16_steps12(v);
         float2 Y[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Y[c] = (v[4 * c] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);   // carrier tid + 256*c
+        for (int c = 0; c < 4; ++c) Y[c] = add2(add2(v[4 * c], v[4 * c + 1]), add2(v[4 * c + 2], v[4 * c + 3]));   // carrier tid + 256*c
         // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
         if (s == 0) {
 #pragma unroll
@@ -236,33 +261,34 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             }
             __syncthreads();
         }
-        // ---- equalise + decide
-        const int sf = s % p.SpF;
+        // ---- equalise + decide (branch-free per carrier; pilots / unused carriers skip the store)
+        {
+            uint8_t* sp = symidx + sf * p.Nd;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int k = tid + 256 * c;
-            const int sl = slot_s[k];
-            if (sl >= 0) {
-                float2 e = (k < p.Nc) ? cmul(Y[c], Hinv[k]) : make_float2(0.f, 0.f);
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t dr = ((c < 2 ? role01 : role23) >> (16 * (c & 1))) & 0xFFFFu;
+                const float2 e = cmul(Y[c], Hinv[tid + 256 * c]);
                 float margin = 1.f;
-                int idx;
-                if (QAM16) idx = demap16<NEAR>(e.x, e.y, two_a, &margin);
-                else idx = nearest_idx(con, e.x, e.y, &margin);
-                if (NEAR && margin < near_eps) ++nears;
-                symidx[sf * p.Nd + sl] = (uint8_t)idx;
+                uint32_t nib;
+                if (QAM16) nib = demap16_nib<NEAR>(e.x, e.y, two_a, &margin);
+                else nib = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                if (dr != 0xFFFFu) {
+                    sp[dr] = (uint8_t)nib;
+                    if (NEAR && margin < near_eps) ++nears;
+                }
             }
         }
         // ---- frame complete: pack, DeScrambler, compare
         if (sf == p.SpF - 1) {
             __syncthreads();
-            const int f = s / p.SpF;
             const int frame_bits = p.frame_words * 32;
             for (int w = tid; w < p.frame_words; w += FX_THREADS) {
                 uint32_t word = 0;
                 if (QAM16) {
-                    const uint8_t* sp = symidx + 8 * w;    // 8 nibbles, each MSB-first inside LSB-first packing
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) word |= (__brev((uint32_t)sp[j]) >> 28) << (4 * j);
+                    const uint2 by = *reinterpret_cast<const uint2*>(symidx + 8 * w);   // 8 ready-made nibbles, one per byte
+                    uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
+                    uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
+                    word = lo | (hi << 16);
                 } else {
                     const int b0 = 32 * w, b1 = b0 + 32;
                     for (int j = b0 / bps; j * bps < b1 && j * bps < frame_bits; ++j) {
@@ -287,7 +313,8 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 if (outbits) outbits[wbase + w] = o;
             }
         }
-        if (s == p.S - 1) {   // stream complete
+        if (++sf == p.SpF) { sf = 0; ++f; }
+        if (++s == p.S) {   // stream complete
             errs = block_sum(errs, red_i);
             if (NEAR) nears = block_sum(nears, red_i);
             if (tid == 0) {
@@ -298,7 +325,8 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 }
                 if (err_stream) err_stream[b] = errs;
             }
-            errs = 0; nears = 0;
+            errs = 0; nears = 0; s = 0; sf = 0; f = 0;
+            b += gridDim.x;
         }
     }
 }
@@ -333,7 +361,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     if (lp->Tg & 1) return OFDM_OK;          // bulk copies need 16-byte aligned symbol starts
     if (((uintptr_t)rx) & 15) return OFDM_OK;
     size_t smem = sizeof(float2) * (2 * 4096 + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 + sizeof(uint32_t) * p.frame_words +
-                  (size_t)lp->SpF * lp->Nd + 16;
+                  (size_t)lp->SpF * lp->Nd + 32;
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
     const bool q16 = lp->constellation == OFDM_16QAM;
     const bool near = near_eps > 0.0;
