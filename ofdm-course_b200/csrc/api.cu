@@ -307,7 +307,7 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
     std::vector<double> band((size_t)nk * bw, 0.0);
     if (spline)
         for (int j = 0; j < nk; ++j)
-            for (int i = clo[j]; i <= chi[j]; ++i) band[(size_t)i * bw + (j - i + hb)] = (double)cols[j][i - clo[j]];
+            for (int i = clo[j]; i <= chi[j]; ++i) band[(size_t)(j - i + hb) * nk + i] = (double)cols[j][i - clo[j]];   // tap-major [bw][nk]
 
     std::vector<double> qw((size_t)nq * 4);
     std::vector<int32_t> qk(nq);
@@ -320,12 +320,12 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
         qk[q] = k;
         if (spline) {
             double t2 = t * t, t3 = t2 * t;
-            qw[4 * q + 0] = 2 * t3 - 3 * t2 + 1;
-            qw[4 * q + 1] = (t3 - 2 * t2 + t) * h;
-            qw[4 * q + 2] = -2 * t3 + 3 * t2;
-            qw[4 * q + 3] = (t3 - t2) * h;
+            qw[q] = 2 * t3 - 3 * t2 + 1;
+            qw[(size_t)nq + q] = (t3 - 2 * t2 + t) * h;
+            qw[(size_t)2 * nq + q] = -2 * t3 + 3 * t2;
+            qw[(size_t)3 * nq + q] = (t3 - t2) * h;
         } else {
-            qw[4 * q + 0] = 1 - t; qw[4 * q + 1] = 0; qw[4 * q + 2] = t; qw[4 * q + 3] = 0;
+            qw[q] = 1 - t; qw[(size_t)nq + q] = 0; qw[(size_t)2 * nq + q] = t; qw[(size_t)3 * nq + q] = 0;
         }
     }
     auto upload_real = [&](const std::vector<double>& v) -> void* {

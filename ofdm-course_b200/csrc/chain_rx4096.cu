@@ -13,6 +13,8 @@
 #include "interp.cuh"
 
 #define FX_THREADS 256
+#define XROW 257          // pass-B output row stride (k1): +1 pad makes pass C's reads bank-conflict free with immediate offsets
+#define XBUF 4112         // samples per symbol buffer: 15*257 + 255 + 1, rounded to 16
 #define SLOT_ZERO (-2147483647 - 1)
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
@@ -80,7 +82,7 @@ template <bool NEAR>
 __device__ __forceinline__ uint32_t demap16_nib(float x, float y, float two_a, float* margin) {
     const float ax = fabsf(x), ay = fabsf(y);
     uint32_t nib = (x > 0.f ? 1u : 0u) | (ax < two_a ? 2u : 0u) | (y < 0.f ? 4u : 0u) | (ay < two_a ? 8u : 0u);
-    if (!(ax <= CUDART_INF_F) || !(ay <= CUDART_INF_F)) nib = 0u;       // NaN in either part
+    if (!(ax + ay <= CUDART_INF_F)) nib = 0u;                             // NaN in either part
     if (NEAR) {
         float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
         *margin = 2.f * two_a * fminf(dx, dy);  // second-best minus best squared distance
@@ -117,26 +119,26 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // prefetched two items ahead into a two-buffer ring by one elected thread; all three FFT passes run
 // in place in the buffer the symbol landed in:
 //   pass A  x[256 n1 + t]            -> same places, index k1 replaces n1          (thread-private)
-//   pass B  [256 k1 + 16 n2 + n3]    -> [256 k1 + 16 k2 + (n3 ^ k1)]                (XOR swizzle)
-//   pass C  reads 16 consecutive (swizzled) n3 per (k1,k2): conflict-free because of the swizzle.
+//   pass B  [256 k1 + 16 n2 + n3]    -> [257 k1 + 16 k2 + n3]                        (row pad of one sample)
+//   pass C  reads 16 consecutive n3 per (k1,k2) with immediate offsets: conflict-free because of the pad.
 template <bool QAM16, bool NEAR>
 __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
                                                                int32_t* __restrict__ err_stream, float near_eps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int red_i[32];
     __shared__ __align__(8) uint64_t bars[2];
     float2* xb0 = (float2*)smem_raw;            // two 4096-sample symbol buffers (ring)
-    float2* Hinv = xb0 + 2 * 4096;              // 1024
+    float2* Hinv = xb0 + 2 * XBUF;              // 1024
     float2* yk = Hinv + 1024;                   // n_knots
     float2* dk = yk + plan.n_knots;             // n_knots
     int32_t* slot_s = (int32_t*)(dk + plan.n_knots);   // 1024
-    uint8_t* symidx = (uint8_t*)(slot_s + 1024);        // SpF*Nd decisions of the current frame (8-byte aligned)
-    uint32_t* raw = (uint32_t*)(symidx + ((p.SpF * p.Nd + 7) & ~7));   // frame_words
+    float2* pinv = (float2*)(slot_s + 1024);            // Np reciprocals of the first-symbol pilots
+    uint8_t* symidx = (uint8_t*)(pinv + p.Np);          // SpF*Nd decisions of the current frame (8-byte aligned)
     const int tid = threadIdx.x;
     const int bps = con.bps;
     for (int i = tid; i < 1024; i += FX_THREADS) slot_s[i] = p.slot[i];
+    for (int i = tid; i < p.Np; i += FX_THREADS) { float2 x = p.pilots[i]; float dd = x.x * x.x + x.y * x.y; pinv[i] = make_float2(x.x / dd, -x.y / dd); }
 
     // per-thread twiddles, resident for the whole kernel
     float2 ta[16], tb[16];
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     if (tid == 0) {
         for (int i = 0; i < 2 && i < n_items; ++i) {
             mbar_expect_tx(&bars[i], 32768u);
-            bulk_g2s(xb0 + i * 4096, pf_ptr, 32768u, &bars[i]);
+            bulk_g2s(xb0 + i * XBUF, pf_ptr, 32768u, &bars[i]);
             pf_advance();
         }
     }
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     uint32_t parity = 0;
     for (int64_t q = 0; q < n_items; ++q) {
         const int cur = (int)(q & 1);
-        float2* X = xb0 + cur * 4096;
+        float2* X = xb0 + cur * XBUF;
         float2 v[16];
         mbar_wait(&bars[cur], parity);
         parity ^= (uint32_t)cur;                   // flips after both buffers have been used once
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
             __syncthreads();                       // every read precedes the swizzled writes
             fft16(v);
-            float2* wp = X + (tid >> 4) * 256 + ((tid & 15) ^ (tid >> 4));
+            float2* wp = X + (tid >> 4) * XROW + (tid & 15);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -227,10 +229,9 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         __syncthreads();
         // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
         {
-            const int k1 = tid & 15;
-            const float2* rp = X + k1 * 256 + (tid >> 4) * 16;
+            const float2* rp = X + (tid & 15) * XROW + (tid >> 4) * 16;
 #pragma unroll
-            for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3 ^ k1];
+            for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3];
         }
         __syncthreads();                           // buffer `cur` is free: refill it with item q+2
         if (tid == 0 && q + 2 < n_items) {
@@ -238,6 +239,12 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             mbar_expect_tx(&bars[cur], 32768u);
             bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
             pf_advance();
+        }
+        uint32_t txw[4] = {0u, 0u, 0u, 0u};
+        if (sf == p.SpF - 1 && txbits) {           // reference words of this frame, consumed ~400 instructions later
+            const uint32_t* tp = txbits + b * stream_words + (int64_t)f * p.frame_words + tid;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = __ldg(tp + FX_THREADS * j);
         }
         fft16_steps12(v);
         float2 Y[4];
@@ -248,7 +255,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int sl = slot_s[tid + 256 * c];
-                if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cdiv(Y[c], p.pilots[pi]); }
+                if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cmul(Y[c], pinv[pi]); }
             }
             __syncthreads();
             plan_apply(plan, yk, dk, Hinv);   // Hinv temporarily holds H (nq = Nc entries)
@@ -278,53 +285,62 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 }
             }
         }
-        // ---- frame complete: pack, DeScrambler, compare
+        // ---- frame complete: pack, DeScrambler, compare (reference words were prefetched before pass C's tail)
         if (sf == p.SpF - 1) {
             __syncthreads();
-            const int frame_bits = p.frame_words * 32;
-            for (int w = tid; w < p.frame_words; w += FX_THREADS) {
-                uint32_t word = 0;
+            const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
+            auto packed = [&](int w) -> uint32_t {
                 if (QAM16) {
                     const uint2 by = *reinterpret_cast<const uint2*>(symidx + 8 * w);   // 8 ready-made nibbles, one per byte
                     uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
                     uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
-                    word = lo | (hi << 16);
-                } else {
-                    const int b0 = 32 * w, b1 = b0 + 32;
-                    for (int j = b0 / bps; j * bps < b1 && j * bps < frame_bits; ++j) {
-                        int idx = symidx[j];
-                        for (int i = 0; i < bps; ++i) {
-                            int pos = j * bps + i;
-                            if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
-                        }
+                    return lo | (hi << 16);
+                }
+                uint32_t word = 0;
+                const int b0 = 32 * w, b1 = b0 + 32;
+                for (int j = b0 / bps; j * bps < b1; ++j) {
+                    int idx = symidx[j];
+                    for (int i = 0; i < bps; ++i) {
+                        int pos = j * bps + i;
+                        if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
                     }
                 }
-                raw[w] = word;
-            }
-            __syncthreads();
-            const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
-            for (int w = tid; w < p.frame_words; w += FX_THREADS) {
-                uint32_t cw = raw[w], o = cw;
-                if (p.scramble) {
-                    uint32_t prev = w ? raw[w - 1] : p.prev0;
-                    o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+                return word;
+            };
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int w = tid + FX_THREADS * j;
+                if (w < p.frame_words) {
+                    const uint32_t cw = packed(w);
+                    uint32_t o = cw;
+                    if (p.scramble) {
+                        const uint32_t prev = w ? packed(w - 1) : p.prev0;
+                        o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+                    }
+                    if (txbits) errs += __popc(o ^ txw[j]);
+                    if (outbits) outbits[wbase + w] = o;
                 }
+            }
+            for (int w = tid + 4 * FX_THREADS; w < p.frame_words; w += FX_THREADS) {   // frames longer than 32 Kbit
+                const uint32_t cw = packed(w);
+                uint32_t o = cw;
+                if (p.scramble) { const uint32_t prev = packed(w - 1); o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18)); }
                 if (txbits) errs += __popc(o ^ txbits[wbase + w]);
                 if (outbits) outbits[wbase + w] = o;
             }
         }
         if (++sf == p.SpF) { sf = 0; ++f; }
-        if (++s == p.S) {   // stream complete
-            errs = block_sum(errs, red_i);
-            if (NEAR) nears = block_sum(nears, red_i);
-            if (tid == 0) {
-                if (counts) {
-                    if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
-                    atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
-                    if (NEAR && nears) atomicAdd(&counts[2], (unsigned long long)nears);
-                }
-                if (err_stream) err_stream[b] = errs;
+        if (++s == p.S) {   // stream complete: one atomic per warp that saw errors, no block barrier
+            const int we = warp_sum(errs);
+            if ((tid & 31) == 0 && we) {
+                if (counts) atomicAdd(&counts[0], (unsigned long long)we);
+                if (err_stream) atomicAdd(&err_stream[b], we);
             }
+            if (NEAR) {
+                const int wn = warp_sum(nears);
+                if ((tid & 31) == 0 && wn && counts) atomicAdd(&counts[2], (unsigned long long)wn);
+            }
+            if (tid == 0 && counts) atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
             errs = 0; nears = 0; s = 0; sf = 0; f = 0;
             b += gridDim.x;
         }
@@ -360,8 +376,8 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     REQUIRE(ctx, p.slot && p.pilots && p.tw4096, "device upload failed");
     if (lp->Tg & 1) return OFDM_OK;          // bulk copies need 16-byte aligned symbol starts
     if (((uintptr_t)rx) & 15) return OFDM_OK;
-    size_t smem = sizeof(float2) * (2 * 4096 + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 + sizeof(uint32_t) * p.frame_words +
-                  (size_t)lp->SpF * lp->Nd + 32;
+    size_t smem = sizeof(float2) * (2 * XBUF + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 +
+                  (size_t)lp->SpF * lp->Nd + sizeof(float2) * (size_t)lp->Np + 32;
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
     const bool q16 = lp->constellation == OFDM_16QAM;
     const bool near = near_eps > 0.0;
@@ -370,6 +386,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
                                         : (near ? rx4096_kernel<false, true> : rx4096_kernel<false, false>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
+    if (err_stream) CUDA_TRY(ctx, cudaMemsetAsync(err_stream, 0, sizeof(int32_t) * B, ctx->stream));
     DevConst<float> con = make_devconst<float>(lp->constellation);
     PlanDev<float> pd = plan_dev<float>(pl);
     kern<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream,

@@ -160,8 +160,8 @@ struct InterpPlan {       // device-resident spline/linear operator for a fixed 
     int nq;               // query points
     int hb;               // half bandwidth of the derivative operator
     double lo_den, lo_mul, hi_den, hi_mul;  // edge extension: slope denominators / distances
-    void* band;           // n_knots x (2hb+1) real (T)
-    void* qw;             // nq x 4 real (T) Hermite weights
+    void* band;           // (2hb+1) x n_knots real (T), tap-major so that threads (= knots) load coalesced
+    void* qw;             // 4 x nq real (T) Hermite weights, one plane per weight
     int32_t* qk;          // nq interval index
 };
 

@@ -39,16 +39,17 @@ __device__ __forceinline__ void plan_apply(const PlanDev<T>& p, cx<T>* y, cx<T>*
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         T ar = 0, ai = 0;
         if (p.hb > 0) {
-            const T* row = p.band + (size_t)i * bw;
+            const T* col = p.band + i;            // band is stored tap-major [bw][n]: coalesced across threads
             int c0 = max(0, p.hb - i), c1 = min(bw, n - i + p.hb);
-            for (int c = c0; c < c1; ++c) { T w = row[c]; C v = y[i - p.hb + c]; ar += w * v.x; ai += w * v.y; }
+#pragma unroll 4
+            for (int c = c0; c < c1; ++c) { T w = col[(size_t)c * n]; C v = y[i - p.hb + c]; ar += w * v.x; ai += w * v.y; }
         }
         d[i] = mk<T>(ar, ai);
     }
     __syncthreads();
     for (int q = threadIdx.x; q < p.nq; q += blockDim.x) {
         int k = p.qk[q];
-        T w0 = p.qw[4 * q], w1 = p.qw[4 * q + 1], w2 = p.qw[4 * q + 2], w3 = p.qw[4 * q + 3];
+        T w0 = p.qw[q], w1 = p.qw[p.nq + q], w2 = p.qw[2 * p.nq + q], w3 = p.qw[3 * p.nq + q];   // four planes [4][nq]
         C y0 = y[k], y1 = y[k + 1], d0 = d[k], d1 = d[k + 1];
         out[q] = mk<T>(w0 * y0.x + w1 * d0.x + w2 * y1.x + w3 * d1.x, w0 * y0.y + w1 * d0.y + w2 * y1.y + w3 * d1.y);
     }
