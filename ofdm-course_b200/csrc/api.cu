@@ -302,6 +302,8 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
             cols[j].assign(col.begin() + lo, col.begin() + hi + 1);
         }
     }
+    const bool fold = spline && (p.ext_lo || p.ext_hi) && nk >= 4;
+    if (fold) hb = std::max(hb, 2);
     p.hb = hb;
     const int bw = 2 * hb + 1;
     std::vector<double> band((size_t)nk * bw, 0.0);
@@ -309,6 +311,20 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
         for (int j = 0; j < nk; ++j)
             for (int i = clo[j]; i <= chi[j]; ++i) band[(size_t)(j - i + hb) * nk + i] = (double)cols[j][i - clo[j]];   // tap-major [bw][nk]
 
+    if (fold) {
+        // y0 = y1*(1+m) - y2*m with m = (loc1-1)/(loc2-loc1) (`interpolate.m:8-9`), likewise at the far end:
+        // substitute into every row so the device operator never touches the two extrapolated knots.
+        auto Bm = [&](int i, int j) -> double& { return band[(size_t)(j - i + hb) * nk + i]; };
+        if (p.ext_lo) {
+            const double m = p.lo_mul / p.lo_den;
+            for (int i = 0; i <= std::min(nk - 1, hb); ++i) { double d0 = Bm(i, 0); Bm(i, 1) += d0 * (1 + m); Bm(i, 2) -= d0 * m; Bm(i, 0) = 0; }
+        }
+        if (p.ext_hi) {
+            const double m = p.hi_mul / p.hi_den;
+            for (int i = std::max(0, nk - 1 - hb); i < nk; ++i) { double dn = Bm(i, nk - 1); Bm(i, nk - 2) += dn * (1 + m); Bm(i, nk - 3) -= dn * m; Bm(i, nk - 1) = 0; }
+        }
+        p.folded = 1;
+    }
     std::vector<double> qw((size_t)nq * 4);
     std::vector<int32_t> qk(nq);
     for (int q = 0; q < nq; ++q) {

@@ -159,6 +159,7 @@ struct InterpPlan {       // device-resident spline/linear operator for a fixed 
     int ext_lo, ext_hi;   // 1 when an extrapolated knot is prepended / appended
     int nq;               // query points
     int hb;               // half bandwidth of the derivative operator
+    int folded;           // 1: the edge extension is folded into the operator (it never reads knots 0 / n-1)
     double lo_den, lo_mul, hi_den, hi_mul;  // edge extension: slope denominators / distances
     void* band;           // (2hb+1) x n_knots real (T), tap-major so that threads (= knots) load coalesced
     void* qw;             // 4 x nq real (T) Hermite weights, one plane per weight
