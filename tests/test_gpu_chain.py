@@ -153,3 +153,20 @@ def test_rx_chain_host_entry(G):
     dc = dev["counts"].cpu().numpy()
     assert counts[0] == dc[0] and counts[1] == dc[1]
     assert torch.equal(ob_h, dev["bits"].cpu()) and torch.equal(H_h, dev["H"].cpu())
+
+
+def test_sweep_counts_do_not_depend_on_the_split(G):
+    """counter-based RNG keyed by global stream id => identical counts for any rank count."""
+    from ofdm_b200 import sweep
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    h, _ = O.get_MP_channel_resp(TAPS5, p.Nfft)
+    snrs = [4.0, 10.0, 16.0]
+    one = sweep.ber_sweep_task5(ctx, lp, snrs, 24, 8, h, seed=3, rank=0, world=1)
+    halves = sum(sweep.ber_sweep_task5(ctx, lp, snrs, 24, 8, h, seed=3, rank=r, world=2) for r in range(2))
+    thirds = sum(sweep.ber_sweep_task5(ctx, lp, snrs, 24, 8, h, seed=3, rank=r, world=3) for r in range(3))
+    assert np.array_equal(one, halves) and np.array_equal(one, thirds)
+    assert np.all(one[:, 1] == 24 * p.stream_bits)
+    ber = one[:, 0] / one[:, 1]
+    assert ber[0] > ber[1] > ber[2] and 0.05 < ber[0] < 0.5
