@@ -151,6 +151,8 @@ class Context:
         lp.reg0_host = reg.ctypes.data_as(_cabi.pu8)
         lp.scramble = 1 if scramble else 0
         lp._keep = keep
+        lp.dataCarriers, lp.pilotCarriers, lp.pilotValues = d, pc, pv.reshape(S, pc.size).T.copy()   # (Np, S)
+        lp.Register, lp.constellation_name = reg, str(constellation)
         lp.bps = {1: 1, 2: 2, 3: 3, 4: 4}[lp.constellation]
         lp.frame_bits = lp.SpF * lp.Nd * lp.bps
         lp.stream_bits = lp.S * lp.Nd * lp.bps
@@ -229,14 +231,16 @@ class Context:
     # ---------------------------------------------------------------- a10-a13
     def add_sto(self, x_dev, nsto):
         B, L = x_dev.shape
-        n = self.real(np.broadcast_to(np.asarray(nsto), (B,)).copy(), torch.int32)
+        n = nsto.to(self.device, torch.int32).contiguous() if isinstance(nsto, torch.Tensor) else \
+            self.real(np.broadcast_to(np.asarray(nsto), (B,)).copy(), torch.int32)
         out = torch.empty_like(x_dev)
         self._chk(self.lib.ofdm_add_sto(self.h, self.p(x_dev), B, L, self.p(n), self.p(out)))
         return out
 
     def add_cfo(self, x_dev, cfo, Nfft):
         B, L = x_dev.shape
-        c = self.real(np.broadcast_to(np.asarray(cfo, dtype=np.float64), (B,)).copy())
+        c = cfo.to(self.device, torch.float64).contiguous() if isinstance(cfo, torch.Tensor) else \
+            self.real(np.broadcast_to(np.asarray(cfo, dtype=np.float64), (B,)).copy())
         out = torch.empty_like(x_dev)
         self._chk(self.lib.ofdm_add_cfo(self.h, self.p(x_dev), B, L, self.p(c), Nfft, self.p(out)))
         return out
@@ -399,6 +403,44 @@ class Context:
         self._chk(self.lib.ofdm_rx_chain_t5(self.h, C.byref(lp), self.p(rx_dev), B, self.p(tx_bits_dev), self.p(out_bits) if want_bits else None,
                                             self.p(H) if want_H else None, self.p(counts), self.p(eps), float(near_eps)))
         return {"bits": out_bits, "H": H, "counts": counts, "err_per_stream": eps}
+
+    def rx_chain_t4(self, lp, rx_dev, tx_bits_dev=None, time_desync=True, freq_desync=True, mp_desync=True, near_eps=0.0):
+        """Task-4 sync + CE chain on B device-resident streams, the calls of `Task 4/Main_model_Task_4.m:277-366` in
+        order: AutoCorrFunction -> add_STO x2 -> add_CFO -> remove_IFO -> OFDM_demodulator -> fine_sync ->
+        estimate_channel -> equalize_signal -> get_payload -> demapping -> DeScrambler -> BER count."""
+        B = rx_dev.shape[0]
+        x = rx_dev.reshape(B, -1)
+        info = {}
+        if time_desync or freq_desync:
+            _, tg, fo, fail = self.cp_autocorr(x, lp.Tg, lp.Nfft)
+            info.update(TgPosition=tg, FreqOffset=fo, fail=fail)
+            if time_desync:
+                x = self.add_sto(x, tg)
+                x = self.add_sto(x, -(lp.Nfft + lp.Tg))
+        if freq_desync:
+            x = self.add_cfo(x, -info["FreqOffset"], lp.Nfft)
+            x, ifo = self.remove_ifo(x, lp.Nfft)
+            info.update(IFO=ifo)
+        grid = self.demodulate(x.reshape(B, lp.S, lp.Nfft + lp.Tg), lp.Nfft, lp.Tg)
+        if time_desync or freq_desync:
+            grid, tau, ph = self.fine_sync(grid, lp.pilotCarriers, lp.pilotValues, time_desync, freq_desync)
+            info.update(tau=tau, phase_shift=ph)
+        if mp_desync:
+            H, _ = self.estimate_channel(grid, np.arange(1, lp.Nfft + 1), lp.pilotCarriers, lp.pilotValues)
+            grid = self.equalize(grid, H, lp.N_carrier)
+            info.update(H=H)
+        iq = self.get_payload(grid, lp.dataCarriers)
+        near = None
+        if near_eps > 0:
+            raw, near = self.demap(iq.reshape(-1), lp.constellation_name, near_eps, want_near=True)
+        else:
+            raw = self.demap(iq.reshape(-1), lp.constellation_name)
+        frames = lp.S // lp.SpF
+        bits = self.scramble(raw, B * frames, lp.frame_bits, lp.Register, descramble=True) if lp.scramble else raw
+        info.update(bits=bits, rx_iq=iq, near=near)
+        if tx_bits_dev is not None:
+            info["counts"] = self.ber_count(tx_bits_dev, bits, B * lp.stream_bits)
+        return info
 
     def rx_chain_t5_host(self, lp, rx_host, B, tx_bits_host=None, out_bits_host=None, H_host=None, chunk=2048):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Returns counts (3 int64)."""

@@ -170,3 +170,42 @@ def test_sweep_counts_do_not_depend_on_the_split(G):
     assert np.all(one[:, 1] == 24 * p.stream_bits)
     ber = one[:, 0] / one[:, 1]
     assert ber[0] > ber[1] > ber[2] and 0.05 < ber[0] < 0.5
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_rx_chain_task4_matches_oracle(G, prec):
+    """Config 2 (M2): the whole Task-4 sync + CE chain, batched on the device, against the oracle per stream."""
+    TAPS4 = [[0, 1], [4, .6], [10, .3]]
+    p = OC.params_task4()
+    ctx = G.default_context(prec)
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(8)
+    cases = [(37, 7.24), (900, 0.24), (150, 12.4), (0, 0.0), (611, 3.3)]
+    B = len(cases)
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    rxs, refs = [], []
+    for b, (sto, cfo) in enumerate(cases):
+        tx, _, _ = OC.tx_chain(p, bits[b], fast=True)
+        rx = OC.impair_task4(p, tx, SNR_dB=28, Time_Delay=sto, Freq_Shift=cfo, taps=TAPS4, rng=rng)
+        rxs.append(rx)
+        refs.append(OC.rx_chain_task4(p, rx, bits[b]))
+    out = ctx.rx_chain_t4(lp, ctx.cplx(np.stack(rxs)), tx_bits_dev=ctx.bits(bits.ravel()), near_eps=1e-3 if prec == "f32" else 1e-9)
+    ctx.sync()
+    tg = out["TgPosition"].cpu().numpy(); ifo = out["IFO"].cpu().numpy()
+    fo = out["FreqOffset"].cpu().numpy(); tau = out["tau"].cpu().numpy(); ph = out["phase_shift"].cpu().numpy()
+    got = ctx.host_bits(out["bits"], B * p.stream_bits).reshape(B, -1)
+    mism = 0
+    for b in range(B):
+        assert tg[b] == refs[b]["TgPosition"] and ifo[b] == refs[b]["IFO"]
+        tol = 1e-9 if prec == "f64" else 2e-5
+        assert abs(fo[b] - refs[b]["FreqOffset"]) < tol and abs(tau[b] - refs[b]["tau"]) < tol
+        assert abs(ph[b] - refs[b]["phase_shift"]) < (1e-7 if prec == "f64" else 2e-3)
+        mism += int(np.sum(got[b] != refs[b]["bits"]))
+    counts = out["counts"].cpu().numpy()
+    assert counts[1] == B * p.stream_bits and counts[0] == int(np.sum(got != bits))
+    if prec == "f64":
+        assert mism == 0
+    else:
+        assert mism <= 3 * p.bps * out["near"]
+    # the reference's own pass criterion (`Main_model_Task_4.m:367`)
+    assert counts[0] / counts[1] < 0.2
