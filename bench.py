@@ -266,7 +266,8 @@ def run_gpu(args, rank, world, local_rank):
         "e2e": {"value": e2e_val, "unit": "symbols/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "traffic": ((traffic or {}).get("dram_bytes_per_symbol") or 0) * syms_per_step or None, "peak_source": peak_src,
+                     "traffic_source": (traffic or {}).get("source"),
                      "kernel": "rx4096_kernel<true>", "algorithmic_bytes_per_symbol": A_M1, "kernel_ms": k_ms},
     }
     if world == 1 and not args.no_cpu:
