@@ -232,6 +232,17 @@ OFDM_API int ofdm_rx_chain_t5_host(ofdm_ctx*, const ofdm_link_params*, const voi
                                    const uint32_t* tx_bits_host, uint32_t* out_bits_host, void* H_host,
                                    int64_t* counts_host, int64_t chunk_streams);
 
+/* M2 RX chain, fused (FP32 contexts): AutoCorrFunction -> add_STO x2 -> add_CFO -> remove_IFO -> OFDM_demodulator ->
+ * fine_sync -> estimate_channel -> equalize_signal -> get_payload -> demapping -> DeScrambler -> BER count
+ * (`Task 4/Main_model_Task_4.m:277-366`), one pass for the autocorrelation plus one persistent kernel.
+ * rx_dev B x S x (Nfft+Tg).  Optional outputs: out_bits_dev, counts_dev {errors, bits, near} += , and the
+ * per-stream estimates tg_dev (int32), fo_dev (double), ifo_dev (int32, -1 = no bin above 0.77), tau_dev,
+ * phase_dev (double), H_dev (B x N_carrier). */
+OFDM_API int ofdm_rx_chain_t4(ofdm_ctx*, const ofdm_link_params*, const void* rx_dev, int64_t B, int time_desync,
+                              int freq_desync, int mp_desync, const uint32_t* tx_bits_dev, uint32_t* out_bits_dev,
+                              int64_t* counts_dev, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev, double* tau_dev,
+                              double* phase_dev, void* H_dev, double near_eps);
+
 #ifdef __cplusplus
 }
 #endif

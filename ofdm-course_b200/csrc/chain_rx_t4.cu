@@ -1,0 +1,310 @@
+// Fused Task-4 RX chain (`Task 4/Main_model_Task_4.m:277-366`), FP32, one persistent CTA per stream:
+//   AutoCorrFunction (sync.cu, one pass)  ->  this kernel:
+//   add_STO(TgPosition), add_STO(-(Nfft+Tg))      as an index offset + zero fill on load      [add_STO.m:5-9]
+//   add_CFO(-FreqOffset), remove_IFO              as ONE rotation exp(-2j*pi*(FFO+IFO)*n/Nfft) [add_CFO.m:6-7, remove_IFO.m:5-9]
+//   OFDM_demodulator                              shared-memory Stockham FFT per symbol        [OFDM_demodulator.m:5-8]
+//   fine_sync                                     estimators in double on the pilots           [Task 4/fine_sync.m:25-58]
+//   estimate_channel + equalize_signal            symbol-averaged pilot LS, not-a-knot spline  [estimate_channel.m:4-8, equalize_signal.m:6]
+//   get_payload, demapping, DeScrambler, BER      per 5-symbol frame (frames are not word aligned: 6,640 bits)
+// The N_carrier useful bins of every symbol are parked in a per-CTA global scratch (stays in L2) between the
+// FFT phase and the decision phase, because fine_sync's estimates need all symbols before any of them is corrected.
+#include "fft.cuh"
+#include "interp.cuh"
+
+const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
+uint32_t ofdm_reg_to_prev(const uint8_t* reg);
+#define T4_THREADS 256
+#define SLOT_ZERO (-2147483647 - 1)
+
+struct T4Params {
+    int Nfft, logN, Tg, Nc, S, SpF, Nd, Np, bps, scramble, frame_bits, frames;
+    int time_desync, freq_desync, mp_desync;
+    uint32_t prev0;
+    const int32_t* data0;      // Nd 0-based data carriers
+    const int32_t* pil0;       // Np 0-based pilot carriers
+    const float2* pilots;      // Np x S column-major (float)
+    const double2* pilots_d;   // same in double for the estimators
+    const float2* tw;          // W_Nfft^k
+};
+
+__device__ __forceinline__ float2 rot_from_cycles(double cyc) {   // exp(-2j*pi*cyc), range-reduced in double
+    double fr = cyc - floor(cyc);
+    float s, c;
+    sincospif((float)(-2.0 * fr), &s, &c);
+    return make_float2(c, s);
+}
+
+__global__ void __launch_bounds__(T4_THREADS) rx_t4_kernel(T4Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx, int64_t B,
+                                                           int64_t L, const int32_t* __restrict__ tg_pos, const double* __restrict__ freq_off,
+                                                           float2* __restrict__ scratch, const uint32_t* __restrict__ txbits, int64_t total_bits,
+                                                           uint32_t* __restrict__ outbits, unsigned long long* __restrict__ counts,
+                                                           int32_t* __restrict__ ifo_out, double* __restrict__ tau_out, double* __restrict__ phase_out,
+                                                           float2* __restrict__ Hout, float near_eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int red_i[32];
+    __shared__ int cnt[T4_THREADS];
+    float2* fa = (float2*)smem_raw;                 // FFT ping-pong
+    float2* fb = fa + p.Nfft;
+    float2* Yp = fb + p.Nfft;                       // pilots of every symbol, [s][p]
+    float2* rot_s = Yp + p.S * p.Np;                // per-symbol base rotation
+    float2* G = rot_s + p.S;                        // per-carrier correction / equaliser, Nc
+    float2* yk = G + p.Nc;                          // spline knots
+    float2* dk = yk + plan.n_knots;
+    double* taus = (double*)(dk + plan.n_knots);    // Np*S differential timing estimates
+    uint32_t* raw = (uint32_t*)(taus + p.S * p.Np); // frame words
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint8_t* symidx = (uint8_t*)(raw + fw);         // SpF * Nd decisions
+    const int tid = threadIdx.x;
+    const int SL = p.Nfft + p.Tg;
+    const int M = p.Np * p.S;
+    float2* Ysc = scratch + (int64_t)blockIdx.x * p.S * p.Nc;   // this CTA's parking area
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    const int NJ = p.Nfft / T4_THREADS;             // samples per thread per symbol (Nfft >= 256)
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const float2* r = rx + b * L;
+        const int tg = p.time_desync ? tg_pos[b] : 0;
+        const double fo = p.freq_desync ? freq_off[b] : 0.0;
+        // sample n of the time-corrected stream (`Main_model_Task_4.m:292-294`)
+        auto sample = [&](int64_t n) -> float2 {
+            if (!p.time_desync) return r[n];
+            int64_t m = n - SL + tg;
+            return (n >= SL && m < L && m >= 0) ? r[m] : make_float2(0.f, 0.f);
+        };
+        // ---- remove_IFO: first bin of |fft(y3(Nfft+1:2*Nfft))| above 0.77 (`remove_IFO.m:5-8`)
+        int ifo = 0;
+        if (p.freq_desync) {
+            for (int i = tid; i < p.Nfft; i += T4_THREADS) {
+                const int64_t n = p.Nfft + i;
+                fa[i] = cmul(sample(n), rot_from_cycles(fo * (double)n / p.Nfft));
+            }
+            __syncthreads();
+            float2* X = block_fft<float, false>(fa, fb, p.Nfft, p.logN, p.tw);
+            int first = 0x7fffffff;
+            for (int i = tid; i < p.Nfft; i += T4_THREADS) {
+                double re = X[i].x, im = X[i].y;
+                if (sqrt(re * re + im * im) > 0.77) { first = i; break; }
+            }
+            first = block_min(first, red_i);
+            ifo = (first == 0x7fffffff) ? -1 : first;
+            __syncthreads();
+        }
+        if (tid == 0 && ifo_out) ifo_out[b] = ifo;
+        const double c = fo + (ifo > 0 ? ifo : 0);   // total derotation in cycles per Nfft samples
+        float2 w[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j < NJ) w[j] = rot_from_cycles(c * (double)(tid + T4_THREADS * j) / p.Nfft);
+        for (int s = tid; s < p.S; s += T4_THREADS) rot_s[s] = rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / p.Nfft);
+        __syncthreads();
+        // ---- OFDM_demodulator for every symbol; park the useful bins, keep the pilots
+        for (int s = 0; s < p.S; ++s) {
+            const int64_t n0 = (int64_t)s * SL + p.Tg;
+            const float2 rs = rot_s[s];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (j < NJ) {
+                    const int i = tid + T4_THREADS * j;
+                    float2 x = sample(n0 + i);
+                    if (p.freq_desync) x = cmul(x, cmul(rs, w[j]));
+                    fa[i] = x;
+                }
+            __syncthreads();
+            float2* X = block_fft<float, false>(fa, fb, p.Nfft, p.logN, p.tw);
+            for (int k = tid; k < p.Nc; k += T4_THREADS) Ysc[(int64_t)s * p.Nc + k] = X[k];
+            for (int q = tid; q < p.Np; q += T4_THREADS) Yp[s * p.Np + q] = X[p.pil0[q]];
+            __syncthreads();
+        }
+        // ---- fine_sync estimators (`Task 4/fine_sync.m:25-35,47-52`), in double
+        double tau = 0.0, phase = 0.0;
+        if (p.time_desync || p.freq_desync) {
+            const double deltak = (double)(p.pil0[1] - p.pil0[0]);
+            auto q_at = [&](int i) -> double2 { return cmulc(p.pilots_d[i], to_d(Yp[i])); };   // tx * conj(rx), flat column-major index
+            auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return atan2(d.y, d.x) / (2.0 * CUDART_PI * deltak); };
+            const int n = M - 1;
+            for (int j = tid; j < n; j += T4_THREADS) taus[j] = tau_at(j);                  // taus(j+1) of the reference (:25-30)
+            __syncthreads();
+            // mask = [false, abs(diffs)<1e-3 & abs(diffs)~=0]; taus_result = taus(mask); mean(taus_result(Np+1:end))  (:32-35)
+            const int CH = (n + T4_THREADS - 1) / T4_THREADS;
+            const int lo = min(tid * CH, n), hi = min(lo + CH, n);
+            int cmask = 0;
+            for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
+            cnt[tid] = cmask;
+            __syncthreads();
+            int rank = 0;
+            for (int k = 0; k < tid; ++k) rank += cnt[k];
+            double sum = 0; int kept = 0;
+            for (int j = max(lo, 1); j < hi; ++j) {
+                double d = fabs(taus[j] - taus[j - 1]);
+                if (d < 1e-3 && d != 0.0) { if (rank >= p.Np) { sum += taus[j]; ++kept; } ++rank; }
+            }
+            sum = block_sum(sum, red);
+            double nk = block_sum((double)kept, red);
+            tau = sum / nk;
+            double ps = 0; int pn = 0;
+            for (int i = tid; i < M; i += T4_THREADS) {
+                const int pq = i % p.Np;
+                double2 rxv = to_d(Yp[i]);
+                if (p.time_desync) { double sn, cs; sincospi(2.0 * tau * (double)p.pil0[pq], &sn, &cs); rxv = cmul(rxv, make_double2(cs, sn)); }
+                double2 qq = cmulc(p.pilots_d[i], rxv);
+                double a = atan2(qq.y, qq.x);
+                if (fabs(a) > 1e-3) { ps += a; ++pn; }
+            }
+            ps = block_sum(ps, red);
+            double pk = block_sum((double)pn, red);
+            phase = ps / pk;
+            if (tid == 0) { if (tau_out) tau_out[b] = tau; if (phase_out) phase_out[b] = phase; }
+        }
+        // ---- per-carrier correction factor exp(j*(2*pi*tau*k*[time] + phase*[freq])) (`fine_sync.m:38-58`)
+        for (int k = tid; k < p.Nc; k += T4_THREADS) {
+            double sn = 0.0, cs = 1.0;
+            if (p.time_desync || p.freq_desync) {
+                double ang = (p.time_desync ? 2.0 * tau * (double)k : 0.0);     // in units of pi
+                double s1, c1, s2 = 0.0, c2 = 1.0;
+                sincospi(ang, &s1, &c1);
+                if (p.freq_desync) sincos(phase, &s2, &c2);
+                cs = c1 * c2 - s1 * s2; sn = s1 * c2 + c1 * s2;
+            }
+            G[k] = make_float2((float)cs, (float)sn);
+        }
+        __syncthreads();
+        // ---- estimate_channel on the corrected grid + equalize_signal (`estimate_channel.m:4-8`)
+        if (p.mp_desync) {
+            for (int q = tid; q < p.Np; q += T4_THREADS) {
+                float sr = 0.f, si = 0.f;
+                const float2 g = G[p.pil0[q]];
+                for (int s = 0; s < p.S; ++s) { float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
+                yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
+            }
+            __syncthreads();
+            float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
+            plan_apply_fn<float>(plan, yk, dk, [&](int k, float2 h) {
+                if (Hrow) Hrow[k] = h;
+                G[k] = cdiv(G[k], h);            // equalised = Y * cf / H
+            });
+            __syncthreads();
+        }
+        // ---- get_payload, demapping, DeScrambler, BER
+        int errs = 0, nears = 0;
+        for (int s = 0; s < p.S; ++s) {
+            const int sf = s % p.SpF;
+            for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
+                const int cidx = p.data0[dr];
+                float2 e = (cidx < p.Nc) ? cmul(Ysc[(int64_t)s * p.Nc + cidx], G[cidx]) : make_float2(0.f, 0.f);
+                float margin;
+                int idx = nearest_idx(con, e.x, e.y, &margin);
+                if (margin < near_eps) ++nears;
+                symidx[sf * p.Nd + dr] = (uint8_t)idx;
+            }
+            __syncthreads();
+            if (sf == p.SpF - 1) {
+                const int f = s / p.SpF;
+                for (int wd = tid; wd < fw; wd += T4_THREADS) {
+                    const int b0 = 32 * wd, b1 = min(b0 + 32, p.frame_bits);
+                    uint32_t word = 0;
+                    for (int q = b0 / p.bps; q * p.bps < b1; ++q) {
+                        int idx = symidx[q];
+                        for (int i = 0; i < p.bps; ++i) {
+                            int pos = q * p.bps + i;
+                            if (pos >= b0 && pos < b1 && ((idx >> (p.bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                        }
+                    }
+                    raw[wd] = word;
+                }
+                __syncthreads();
+                const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+                for (int wd = tid; wd < fw; wd += T4_THREADS) {
+                    uint32_t cw = raw[wd], o = cw;
+                    if (p.scramble) {
+                        uint32_t prev = wd ? raw[wd - 1] : p.prev0;
+                        o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+                    }
+                    const int n = min(32, p.frame_bits - 32 * wd);
+                    if (n < 32) o &= (1u << n) - 1u;
+                    if (txbits) errs += __popc(o ^ bits_get32(txbits, base + 32 * (int64_t)wd, min(total_bits, base + p.frame_bits)));
+                    if (outbits) bits_put(outbits, base + 32 * (int64_t)wd, n, o);
+                }
+                __syncthreads();
+            }
+        }
+        errs = block_sum(errs, red_i);
+        nears = block_sum(nears, red_i);
+        if (tid == 0 && counts) {
+            if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+            atomicAdd(&counts[1], (unsigned long long)stream_bits);
+            if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_t L, int W, int Nfft, void* autocorr, int32_t* tg_pos, double* freq_off,
+                                int32_t* fail);
+
+extern "C" int ofdm_rx_chain_t4(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, int time_desync, int freq_desync, int mp_desync,
+                                const uint32_t* tx_bits, uint32_t* out_bits, int64_t* counts, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev,
+                                double* tau_dev, double* phase_dev, void* H_dev, double near_eps) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, lp && rx && B >= 0, "bad argument");
+    REQUIRE(ctx, ctx->precision == OFDM_PREC_F32, "the fused Task-4 chain is FP32 only (compose the per-function calls in FP64 mode)");
+    REQUIRE(ctx, is_pow2(lp->Nfft) && lp->Nfft >= 256 && lp->Nfft <= 2048, "fused Task-4 chain supports Nfft = 256..2048");
+    REQUIRE(ctx, lp->S > 0 && lp->SpF > 0 && lp->S % lp->SpF == 0 && lp->Np >= 2 && lp->Nd >= 1 && lp->N_carrier >= 2 && lp->N_carrier <= lp->Nfft, "bad link parameters");
+    if (B == 0) return OFDM_OK;
+    ConstTable ct = host_constellation(lp->constellation);
+    REQUIRE(ctx, ct.bps > 0, "unknown constellation");
+    const int64_t L = (int64_t)lp->S * (lp->Nfft + lp->Tg);
+    T4Params p;
+    p.Nfft = lp->Nfft; p.logN = ilog2(lp->Nfft); p.Tg = lp->Tg; p.Nc = lp->N_carrier; p.S = lp->S; p.SpF = lp->SpF; p.Nd = lp->Nd; p.Np = lp->Np;
+    p.bps = ct.bps; p.scramble = lp->scramble; p.frame_bits = lp->SpF * lp->Nd * ct.bps; p.frames = lp->S / lp->SpF;
+    p.time_desync = time_desync != 0; p.freq_desync = freq_desync != 0; p.mp_desync = mp_desync != 0;
+    p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
+    std::vector<int32_t> d0(lp->Nd), p0(lp->Np);
+    for (int i = 0; i < lp->Nd; ++i) { REQUIRE(ctx, lp->data_carriers_host[i] >= 1 && lp->data_carriers_host[i] <= lp->Nfft, "data carrier out of range"); d0[i] = lp->data_carriers_host[i] - 1; }
+    for (int i = 0; i < lp->Np; ++i) {
+        REQUIRE(ctx, lp->pilot_carriers_host[i] >= 1 && lp->pilot_carriers_host[i] <= lp->N_carrier, "pilot carrier out of range");
+        REQUIRE(ctx, i == 0 || lp->pilot_carriers_host[i] > lp->pilot_carriers_host[i - 1], "pilot carriers must increase");
+        p0[i] = lp->pilot_carriers_host[i] - 1;
+    }
+    p.data0 = (const int32_t*)ctx_blob(ctx, d0.data(), sizeof(int32_t) * d0.size());
+    p.pil0 = (const int32_t*)ctx_blob(ctx, p0.data(), sizeof(int32_t) * p0.size());
+    p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, (size_t)lp->Np * lp->S);
+    p.pilots_d = (const double2*)ctx_blob(ctx, lp->pilot_vals_host, sizeof(double) * 2 * (size_t)lp->Np * lp->S);
+    p.tw = (const float2*)ctx_twiddles(ctx, lp->Nfft);
+    std::vector<int32_t> q(lp->N_carrier);
+    for (int i = 0; i < lp->N_carrier; ++i) q[i] = i + 1;
+    const InterpPlan* pl = ctx_plan(ctx, lp->pilot_carriers_host, lp->Np, 0, q.data(), lp->N_carrier, OFDM_INTERP_SPLINE);   // interp1 over the carriers, no edge extension
+    REQUIRE(ctx, p.data0 && p.pil0 && p.pilots && p.pilots_d && p.tw && pl, "device upload failed");
+    const int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
+    // scratch: [estimates: tg int32 | fo double] + per-CTA parking area
+    const size_t park = sizeof(float2) * (size_t)grid * lp->S * lp->N_carrier;
+    const size_t est = (sizeof(double) + sizeof(int32_t) * 2) * (size_t)B + 64;
+    unsigned char* scr = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&scr, park + est, ctx->stream));
+    double* fo_s = (double*)(scr + park);
+    int32_t* tg_s = (int32_t*)(fo_s + B);
+    if (!fo_dev) fo_dev = fo_s;
+    if (!tg_dev) tg_dev = tg_s;
+    int rc = OFDM_OK;
+    if (time_desync || freq_desync) rc = ofdm_cp_autocorr(ctx, rx, B, L, lp->Tg, lp->Nfft, nullptr, tg_dev, fo_dev, nullptr);
+    if (rc == OFDM_OK) {
+        const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+        if (out_bits && (stream_bits % 32 != 0 || p.frame_bits % 32 != 0)) {
+            cudaError_t e = cudaMemsetAsync(out_bits, 0, sizeof(uint32_t) * OFDM_BIT_WORDS(B * stream_bits), ctx->stream);
+            if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "memset failed: %s", cudaGetErrorString(e));
+        }
+        const int fw = (p.frame_bits + 31) / 32;
+        size_t smem = sizeof(float2) * (2 * (size_t)p.Nfft + (size_t)p.S * p.Np + p.S + p.Nc + 2 * (size_t)pl->n_knots) + sizeof(double) * (size_t)p.S * p.Np + sizeof(uint32_t) * fw + (size_t)p.SpF * p.Nd + 32;
+        if (rc == OFDM_OK && smem > 200 * 1024) rc = ctx_fail(ctx, OFDM_ERR_UNSUPPORTED, "stream shape needs %zu bytes of shared memory", smem);
+        if (rc == OFDM_OK) {
+            cudaFuncSetAttribute(rx_t4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            rx_t4_kernel<<<grid, T4_THREADS, smem, ctx->stream>>>(p, plan_dev<float>(pl), make_devconst<float>(lp->constellation), (const float2*)rx, B, L, tg_dev, fo_dev,
+                                                                   (float2*)scr, tx_bits, B * stream_bits, out_bits, (unsigned long long*)counts, ifo_dev, tau_dev,
+                                                                   phase_dev, (float2*)H_dev, (float)near_eps);
+            ctx->launches++;
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "rx_t4_kernel launch failed: %s", cudaGetErrorString(e));
+        }
+    }
+    cudaFreeAsync(scr, ctx->stream);
+    return rc;
+}

@@ -442,6 +442,25 @@ class Context:
             info["counts"] = self.ber_count(tx_bits_dev, bits, B * lp.stream_bits)
         return info
 
+    def rx_chain_t4_fused(self, lp, rx_dev, tx_bits_dev=None, time_desync=True, freq_desync=True, mp_desync=True, near_eps=0.0, want_bits=True,
+                          want_H=False):
+        """Same chain as :meth:`rx_chain_t4` through the fused C entry ``ofdm_rx_chain_t4`` (FP32 contexts)."""
+        B = rx_dev.shape[0]
+        dev = self.device
+        out_bits = self.zeros_words(B * lp.stream_bits) if want_bits else None
+        counts = torch.zeros(3, dtype=torch.int64, device=dev)
+        tg = torch.zeros(B, dtype=torch.int32, device=dev)
+        fo = torch.zeros(B, dtype=torch.float64, device=dev)
+        ifo = torch.zeros(B, dtype=torch.int32, device=dev)
+        tau = torch.zeros(B, dtype=torch.float64, device=dev)
+        ph = torch.zeros(B, dtype=torch.float64, device=dev)
+        H = self.empty_c(B, lp.N_carrier) if want_H else None
+        self._chk(self.lib.ofdm_rx_chain_t4(self.h, C.byref(lp), self.p(rx_dev), B, int(bool(time_desync)), int(bool(freq_desync)), int(bool(mp_desync)),
+                                            self.p(tx_bits_dev), self.p(out_bits), self.p(counts), self.p(tg), self.p(fo), self.p(ifo), self.p(tau),
+                                            self.p(ph), self.p(H), float(near_eps)))
+        return {"bits": out_bits, "counts": counts, "TgPosition": tg, "FreqOffset": fo, "IFO": ifo, "tau": tau, "phase_shift": ph, "H": H,
+                "near": counts[2]}
+
     def rx_chain_t5_host(self, lp, rx_host, B, tx_bits_host=None, out_bits_host=None, H_host=None, chunk=2048):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Returns counts (3 int64)."""
         counts = np.zeros(3, dtype=np.int64)

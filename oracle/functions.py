@@ -331,6 +331,8 @@ def interp1_spline(x, y, xq):
     xq = np.asarray(xq, dtype=np.float64)
     if x.size == 2:
         return y[0] + (y[1] - y[0]) * (xq - x[0]) / (x[1] - x[0])
+    if not np.all(np.isfinite(y)):          # MATLAB propagates NaN through the spline; SciPy refuses it
+        return np.full(xq.shape, np.nan + 1j * np.nan if np.iscomplexobj(y) else np.nan)
     cs = CubicSpline(x, y, bc_type="not-a-knot", extrapolate=True)
     return cs(xq)
 

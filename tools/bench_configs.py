@@ -64,6 +64,16 @@ def main():
                                   "GBps_algorithmic": 9548 * syms / ms / 1e6, "frac_of_measured_hbm": 9548 * syms / ms / 1e6 / PEAK,
                                   "ber": float(cnt[0]) / float(cnt[1]), "note": "13 kernels composed on the device, not yet fused"}
 
+    def m2f():
+        res["f"] = ctx.rx_chain_t4_fused(lp, rx, tx_bits_dev=bits)
+    ms = timed(m2f)
+    cntf = res["f"]["counts"].cpu().numpy()
+    out["M2_task4_sync_chain_fused"] = {"streams": B, "symbols": syms, "ms": ms, "symbols_per_s": syms / ms * 1e3, "algorithmic_B_per_symbol": 9548,
+                                        "GBps_algorithmic": 9548 * syms / ms / 1e6, "frac_of_measured_hbm": 9548 * syms / ms / 1e6 / PEAK,
+                                        "ber": float(cntf[0]) / float(cntf[1]), "note": "autocorr (2 kernels) + one persistent fused kernel"}
+    ms_ac = timed(lambda: ctx.cp_autocorr(rx, p.T_Guard, p.Nfft))
+    out["M2_task4_sync_chain_fused"]["autocorr_ms"] = ms_ac
+
     # ---------------- M3: LS / MMSE + interpolate + equalise on post-FFT grids
     for comb in (4, 1):
         if comb == 1:
