@@ -10,83 +10,89 @@
 // second run to exist (else the reference's catch branch: TgPosition = 65), and evaluates
 // FreqOffset = -angle(rho(TgPosition))/(2*pi) from a directly summed window.
 // =====================================================================================
-#define AC_TILE 1024
-#define AC_THREADS 256
+#define AC_THREADS 128
+#define AC_G 16            // samples per group / per thread
 
-template <typename T>
-__global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out,
+// Window sums WITHOUT subtraction (so all-zero windows are exactly 0 and give the reference's 0/0 = NaN, and no
+// cancellation error is introduced): with 16-sample groups, the window [n, n+W) starting at n = 16a + r is
+//   suffix_a[r] + G[a+1] + ... + G[ge-1] + prefix_ge[oe-1],   ge = (n+W)>>4, oe = (n+W)&15.
+// One thread owns one group: it keeps the suffix sums in registers and leaves the prefix sums in shared memory.
+template <typename T, bool ALIGNED>
+__global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out, int tile,
                                                               cx<T>* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NE = AC_THREADS * AC_G;                 // samples staged per block
+    const int PADN = NE + NE / AC_G;                  // one pad word per group: group stride 17 -> conflict-free
+    T* Qre = (T*)smem_raw;
+    T* Qim = Qre + PADN;
+    T* Qa = Qim + PADN;
+    T* Qb = Qa + PADN;
     const int64_t b = blockIdx.x;
-    const int64_t n0 = (int64_t)blockIdx.y * AC_TILE;
-    const int tile = (int)min((int64_t)AC_TILE, n_out - n0);
-    const int M = tile + W - 1;
-    double* Sre = (double*)smem_raw;
-    double* Sim = Sre + (AC_TILE + W);
-    double* Sa = Sim + (AC_TILE + W);
-    double* Sb = Sa + (AC_TILE + W);
-    __shared__ double wtot[4][AC_THREADS / 32];
-    __shared__ double tot[4][AC_THREADS];
+    const int64_t n0 = (int64_t)blockIdx.y * tile;
     const cx<T>* r = rx + b * L;
     const int tid = threadIdx.x;
-    for (int i = tid; i < M; i += AC_THREADS) {
-        cx<T> x = r[n0 + i], y = r[n0 + i + Nfft];
-        double xr = x.x, xi = x.y, yr = y.x, yi = y.y;
-        Sre[i] = xr * yr + xi * yi;     // x * conj(y)
-        Sim[i] = xi * yr - xr * yi;
-        Sa[i] = xr * xr + xi * xi;
-        Sb[i] = yr * yr + yi * yi;
+    for (int i = tid; i < NE; i += AC_THREADS) {
+        const int64_t n = n0 + i;
+        cx<T> x = mk<T>(0, 0), y = mk<T>(0, 0);
+        if (n + Nfft < L) { x = r[n]; y = r[n + Nfft]; }
+        const int q = i + (i >> 4);
+        Qre[q] = x.x * y.x + x.y * y.y;               // x * conj(y)
+        Qim[q] = x.y * y.x - x.x * y.y;
+        Qa[q] = x.x * x.x + x.y * x.y;
+        Qb[q] = y.x * y.x + y.y * y.y;
     }
     __syncthreads();
-    // chunked inclusive scan: odd chunk length keeps the strided shared accesses conflict-free
-    int CH = (M + AC_THREADS - 1) / AC_THREADS;
-    CH |= 1;
-    const int lo = min(tid * CH, M), hi = min(lo + CH, M);
-    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    for (int i = lo; i < hi; ++i) {
-        t0 += Sre[i]; Sre[i] = t0;
-        t1 += Sim[i]; Sim[i] = t1;
-        t2 += Sa[i]; Sa[i] = t2;
-        t3 += Sb[i]; Sb[i] = t3;
-    }
-    // Offsets of the chunks.  They must come from ONE fixed summation order: a run of exactly-zero
-    // samples (STO zero fill) then leaves the prefix bit-identical on both sides of a window, so the
-    // window sums are exactly 0 and 0/0 gives the reference's NaN (`AutoCorrFunction.m:6`).
-    const int lane = tid & 31, w = tid >> 5;
-    tot[0][tid] = t0; tot[1][tid] = t1; tot[2][tid] = t2; tot[3][tid] = t3;
-    __syncthreads();
-    if (tid < 4 * (AC_THREADS / 32)) {            // one thread per (quantity, warp): sequential lane scan
-        const int q = tid & 3, ww = tid >> 2;
-        double run = 0;
-        for (int l = 0; l < 32; ++l) { double x = tot[q][ww * 32 + l]; tot[q][ww * 32 + l] = run; run += x; }
-        wtot[q][ww] = run;
-    }
-    __syncthreads();
-    double off[4];
+    // own group: suffix sums to registers, prefix sums back to shared memory
+    T s0[AC_G], s1[AC_G], s2[AC_G], s3[AC_G];
+    {
+        const int q0 = tid * (AC_G + 1);
+        T v0[AC_G], v1[AC_G], v2[AC_G], v3[AC_G];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        double base = 0;
-        for (int k = 0; k < w; ++k) base += wtot[q][k];
-        off[q] = base + tot[q][tid];
+        for (int i = 0; i < AC_G; ++i) { v0[i] = Qre[q0 + i]; v1[i] = Qim[q0 + i]; v2[i] = Qa[q0 + i]; v3[i] = Qb[q0 + i]; }
+        T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int i = AC_G - 1; i >= 0; --i) { a0 += v0[i]; a1 += v1[i]; a2 += v2[i]; a3 += v3[i]; s0[i] = a0; s1[i] = a1; s2[i] = a2; s3[i] = a3; }
+        a0 = a1 = a2 = a3 = 0;
+#pragma unroll
+        for (int i = 0; i < AC_G; ++i) { a0 += v0[i]; a1 += v1[i]; a2 += v2[i]; a3 += v3[i]; Qre[q0 + i] = a0; Qim[q0 + i] = a1; Qa[q0 + i] = a2; Qb[q0 + i] = a3; }
     }
-    for (int i = lo; i < hi; ++i) { Sre[i] += off[0]; Sim[i] += off[1]; Sa[i] += off[2]; Sb[i] += off[3]; }
     __syncthreads();
-    for (int j0 = 0; j0 < AC_TILE; j0 += AC_THREADS) {
-        const int j = j0 + tid;
-        bool flag = false;
-        if (j < tile) {
-            double nr = Sre[j + W - 1], ni = Sim[j + W - 1], pa = Sa[j + W - 1], pb = Sb[j + W - 1];
-            if (j > 0) { nr -= Sre[j - 1]; ni -= Sim[j - 1]; pa -= Sa[j - 1]; pb -= Sb[j - 1]; }
-            double den = sqrt(pa * pb);
-            double ar = nr / den, ai = ni / den;   // 0/0 -> NaN as in MATLAB
-            const int64_t n = n0 + j;
-            if (ac_out) ac_out[b * n_out + n] = mk<T>((T)ar, (T)ai);
-            double amp = sqrt(ar * ar + ai * ai);
-            flag = (amp > 0.77) && (n + 1 > (int64_t)W);   // :10-13 (NaN compares false)
+    const int wq = W >> 4, wr = W & 15;
+    uint32_t mask16 = 0;
+    if (tid * AC_G < tile) {
+        // groups a+1 .. a+wq-1 are always fully inside the window; group a+wq is inside when r + wr >= 16
+        T m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        for (int j = tid + 1; j < tid + wq; ++j) { const int q = j * (AC_G + 1) + AC_G - 1; m0 += Qre[q]; m1 += Qim[q]; m2 += Qa[q]; m3 += Qb[q]; }
+        const int qg = (tid + wq) * (AC_G + 1);
+        const T g0 = Qre[qg + AC_G - 1], g1 = Qim[qg + AC_G - 1], g2 = Qa[qg + AC_G - 1], g3 = Qb[qg + AC_G - 1];
+        const int64_t nb = n0 + tid * AC_G;
+        const bool full = (nb + AC_G <= n_out) && (nb + 1 > (int64_t)W);     // uniform for all but the edge groups
+#pragma unroll
+        for (int rr = 0; rr < AC_G; ++rr) {
+            T nr = s0[rr] + m0, ni = s1[rr] + m1, pa = s2[rr] + m2, pb = s3[rr] + m3;
+            if (ALIGNED) {                             // W % 16 == 0: the window ends at offset rr of group a + wq
+                if (rr > 0) { nr += Qre[qg + rr - 1]; ni += Qim[qg + rr - 1]; pa += Qa[qg + rr - 1]; pb += Qb[qg + rr - 1]; }
+            } else {
+                int oe = rr + wr;                      // offset of the window end inside its group
+                int qt = qg;
+                if (oe >= AC_G) { nr += g0; ni += g1; pa += g2; pb += g3; oe -= AC_G; qt += AC_G + 1; }
+                if (oe > 0) { nr += Qre[qt + oe - 1]; ni += Qim[qt + oe - 1]; pa += Qa[qt + oe - 1]; pb += Qb[qt + oe - 1]; }
+            }
+            const int64_t n = nb + rr;
+            // |rho| > 0.77  <=>  |num|^2 > 0.77^2 * pa * pb : no division, and 0 > 0 is false exactly where MATLAB's
+            // 0/0 = NaN fails the comparison (`AutoCorrFunction.m:6,10-12`)
+            const bool above = (nr * nr + ni * ni) > (T)(0.77 * 0.77) * (pa * pb);
+            if (above && (full || (n < n_out && n + 1 > (int64_t)W))) mask16 |= 1u << rr;
+            if (ac_out && n < n_out) {
+                const T den = sqrt(pa * pb);
+                ac_out[b * n_out + n] = mk<T>(nr / den, ni / den);   // 0/0 -> NaN as in MATLAB
+            }
         }
-        unsigned bal = __ballot_sync(0xffffffffu, flag);
-        const int base = j0 + (tid & ~31);   // first output of this warp's 32-wide word (n0 is a multiple of 32)
-        if (lane == 0 && base < tile) flags[b * flag_words + ((n0 + base) >> 5)] = bal;
+    }
+    const uint32_t hi = __shfl_down_sync(0xffffffffu, mask16, 1);
+    if ((tid & 1) == 0 && tid * AC_G < tile) {
+        const int64_t wi = (n0 + tid * AC_G) >> 5;
+        if (wi < flag_words) flags[b * flag_words + wi] = mask16 | (hi << 16);
     }
 }
 
@@ -154,12 +160,15 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
     const int64_t flag_words = (n_out + 31) / 32;
     uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words);
     REQUIRE(ctx, flags != nullptr, "scratch allocation failed");
-    const int tiles = (int)cdiv64(n_out, AC_TILE);
-    size_t smem = 4 * sizeof(double) * (AC_TILE + W);
+    REQUIRE(ctx, W >= AC_G, "window narrower than 16 samples");
+    // outputs per block: every output needs groups a .. a + W/16 + 1 staged; keep the group count even (32-bit flag words)
+    const int tile = AC_G * ((AC_THREADS - (W >> 4) - 2) & ~1);
+    const int tiles = (int)cdiv64(n_out, tile);
     DISPATCH_T(ctx, {
-        auto k1 = autocorr_kernel<T>;
+        size_t smem = 4 * sizeof(T) * (size_t)(AC_THREADS * AC_G + AC_THREADS);
+        auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
         if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_out, (cx<T>*)autocorr, flags, flag_words);
+        k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_out, tile, (cx<T>*)autocorr, flags, flag_words);
         ctx->launches++;
         autocorr_detect_kernel<T><<<(unsigned)cdiv64(B * 32, 128), 128, 0, ctx->stream>>>((const cx<T>*)rx, B, L, W, Nfft, n_out, flags, flag_words,
                                                                                             tg_pos, freq_off, fail);
