@@ -245,7 +245,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * Be * S * e2e_steps / e2e_s
-    h2d = rx_h.numel() * 8 + tb_h.numel() * 4
+    h2d = Be * S * p.Nfft * 8 + tb_h.numel() * 4      # the host entry leaves the cyclic prefix on the host (strided H2D copy)
     d2h = ob_h.numel() * 4 + H_h.numel() * 8 + 24
 
     if rank != 0:
