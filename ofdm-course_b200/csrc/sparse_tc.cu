@@ -1,0 +1,237 @@
+// OMP_estimate on tensor cores for large batches with a dense dictionary (`Task 5/OMP_estimate.m:7,14`):
+// per iteration the correlation A^H r of ALL frames is one tcgen05 GEMM (TF32 in, FP32 accumulate in TMEM) whose
+// epilogue keeps the 4 best |a_l^H r|^2 per frame (tc_gemm.cuh); a SIMT step kernel then re-scores those
+// candidates in FP32/double, so the tensor cores only *screen* and the selected index is the exact FP32 argmax
+// (frames whose TF32 top-4 is not clearly separated fall back to the exact full search).  The rest of the
+// iteration -- pinv via the Gram matrix and a double Cholesky, residual, the 1e-2 stopping rule -- is the same
+// arithmetic as the SIMT pursuit kernel in sparse.cu.
+#include "pursuit_common.cuh"
+#include "tc_gemm.cuh"
+
+#define TS_THREADS 128
+#define TS_DONE 0x40000000
+
+// B operand: row 2l = [Re a_l | Im a_l], row 2l+1 = [-Im a_l | Re a_l], zero padded to K2 columns / 2*Lpad rows
+__global__ void tc_dict_kernel(const float2* __restrict__ A, int Np, int Ldict, int K2, float* __restrict__ Bt) {
+    const int l = blockIdx.x;
+    float* r0 = Bt + (size_t)(2 * l) * K2;
+    float* r1 = r0 + K2;
+    for (int i = threadIdx.x; i < K2; i += blockDim.x) {
+        float v0 = 0.f, v1 = 0.f;
+        if (l < Ldict) {
+            if (i < Np) { float2 a = A[(size_t)l * Np + i]; v0 = a.x; v1 = -a.y; }
+            else if (i < 2 * Np) { float2 a = A[(size_t)l * Np + i - Np]; v0 = a.y; v1 = a.x; }
+        }
+        r0[i] = v0; r1[i] = v1;
+    }
+}
+// A operand: row f = [Re r_f | Im r_f]; starts as the measurement
+__global__ void tc_init_kernel(const float2* __restrict__ Y, int64_t B, int Np, int K2, float* __restrict__ Rt, int32_t* __restrict__ nsel) {
+    const int64_t f = blockIdx.x;
+    float* row = Rt + f * K2;
+    for (int i = threadIdx.x; i < K2; i += blockDim.x) {
+        float v = 0.f;
+        if (f < B) { if (i < Np) v = Y[f * Np + i].x; else if (i < 2 * Np) v = Y[f * Np + i - Np].y; }
+        row[i] = v;
+    }
+    if (threadIdx.x == 0 && f < B) nsel[f] = 0;
+}
+
+// One OMP iteration for one frame.
+__global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* __restrict__ Y, const float2* __restrict__ A, int Np, int Ldict, int K2, int it,
+                                                                 const int32_t* __restrict__ cand, const float* __restrict__ cand_score,
+                                                                 float* __restrict__ Rt, int32_t* __restrict__ sel_g, int32_t* __restrict__ nsel_g,
+                                                                 float2* __restrict__ xs_g, int K, int32_t* __restrict__ fallbacks) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ float sval[32];
+    __shared__ int sidx[32];
+    __shared__ int sel[PU_MAXK], uniq[PU_MAXK], ucol[PU_MAXK], umult[PU_MAXK];
+    __shared__ double2 G[PU_MAXK][PU_MAXK], Lm[PU_MAXK][PU_MAXK], grhs[PU_MAXK], xu[PU_MAXK];
+    const int64_t f = blockIdx.x;
+    const int tid = threadIdx.x;
+    int nsel = nsel_g[f];
+    if (nsel & TS_DONE) return;                         // stopped by the 1e-2 rule in an earlier iteration
+    float2* r = (float2*)smem_raw;
+    float2* yv = r + Np;
+    float* row = Rt + f * K2;
+    for (int i = tid; i < Np; i += TS_THREADS) { r[i] = make_float2(row[i], row[Np + i]); yv[i] = Y[f * Np + i]; }
+    for (int q = tid; q < nsel; q += TS_THREADS) sel[q] = sel_g[f * K + q];
+    __syncthreads();
+    // ---- exact FP32 re-scoring of the screened candidates (first maximum wins, as MATLAB's max)
+    int col;
+    {
+        const float s0 = cand_score[f * TC_TOP], s3 = cand_score[f * TC_TOP + TC_TOP - 1];
+        float best = -CUDART_INF_F; int bi = 0x7fffffff;
+        if (s3 < 0.98f * s0 && s0 > 0.f) {
+            for (int c = 0; c < TC_TOP; ++c) {
+                const int l = cand[f * TC_TOP + c];
+                const float2* a = A + (size_t)l * Np;
+                double2 acc = make_double2(0, 0);
+                for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(r[i]), to_d(a[i]));     // conj(a) * r
+                acc = block_csum(acc, red);
+                const float m = (float)(acc.x * acc.x + acc.y * acc.y);
+                if (m > best || (m == best && l < bi)) { best = m; bi = l; }
+            }
+        } else {                                        // TF32 ranking too close to call: exact search over every column
+            if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1);
+            for (int l = tid; l < Ldict; l += TS_THREADS) {
+                const float2* a = A + (size_t)l * Np;
+                float ar = 0, ai = 0;
+                for (int i = 0; i < Np; ++i) { float2 av = a[i], v = r[i]; ar += av.x * v.x + av.y * v.y; ai += av.x * v.y - av.y * v.x; }
+                const float m = ar * ar + ai * ai;
+                if (m > best) { best = m; bi = l; }
+            }
+            block_argmax(best, bi, sval, sidx);
+        }
+        col = (bi == 0x7fffffff) ? 0 : bi;
+    }
+    // ---- unique columns so far (duplicates share one unknown: pinv's minimum-norm split)
+    if (tid == 0) {
+        sel[nsel] = col;
+        int nu = 0;
+        for (int q = 0; q <= nsel; ++q) {
+            int slot = -1;
+            for (int u = 0; u < nu; ++u) if (ucol[u] == sel[q]) slot = u;
+            if (slot < 0) { ucol[nu] = sel[q]; umult[nu] = 1; uniq[q] = nu; ++nu; } else { umult[slot] += 1; uniq[q] = slot; }
+        }
+        sidx[0] = nu;
+    }
+    __syncthreads();
+    const int nu = sidx[0];
+    nsel += 1;
+    // ---- Gram matrix and right-hand side in double, x = pinv(A_sel) * y
+    for (int q = 0; q < nu; ++q)
+        for (int j = q; j < nu; ++j) {
+            const float2* aq = A + (size_t)ucol[q] * Np;
+            const float2* aj = A + (size_t)ucol[j] * Np;
+            double2 acc = make_double2(0, 0);
+            for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(aj[i]), to_d(aq[i]));       // conj(a_q) * a_j
+            acc = block_csum(acc, red);
+            if (tid == 0) { G[q][j] = acc; G[j][q] = cconj(acc); }
+        }
+    for (int q = 0; q < nu; ++q) {
+        const float2* aq = A + (size_t)ucol[q] * Np;
+        double2 acc = make_double2(0, 0);
+        for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(yv[i]), to_d(aq[i]));
+        acc = block_csum(acc, red);
+        if (tid == 0) grhs[q] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        chol_solve(nu, G, grhs, xu, Lm);
+        for (int q = 0; q < nsel; ++q) { double2 v = cscale(xu[uniq[q]], 1.0 / (double)umult[uniq[q]]); xs_g[f * K + q] = make_float2((float)v.x, (float)v.y); }
+        sel_g[f * K + nsel - 1] = col;
+    }
+    __syncthreads();
+    // ---- residue = y - A*x and the stopping rule (`OMP_estimate.m:18-22`)
+    double dn = 0, on = 0;
+    for (int i = tid; i < Np; i += TS_THREADS) {
+        double2 acc = to_d(yv[i]);
+        for (int q = 0; q < nu; ++q) acc = acc - cmul(to_d(A[(size_t)ucol[q] * Np + i]), xu[q]);
+        const double2 old = to_d(r[i]);
+        dn += (acc.x - old.x) * (acc.x - old.x) + (acc.y - old.y) * (acc.y - old.y);
+        on += old.x * old.x + old.y * old.y;
+        row[i] = (float)acc.x; row[Np + i] = (float)acc.y;
+    }
+    dn = block_sum(dn, red);
+    on = block_sum(on, red);
+    if (tid == 0) nsel_g[f] = nsel | ((it >= 1 && sqrt(dn) / sqrt(on) < 1e-2) ? TS_DONE : 0);
+}
+
+// h(index(i1)) = x(i1) in selection order (later duplicates overwrite), H = fft(h) as a K-term sum
+__global__ void __launch_bounds__(TS_THREADS) omp_tc_finish_kernel(const int32_t* __restrict__ sel_g, const int32_t* __restrict__ nsel_g, const float2* __restrict__ xs_g,
+                                                                   int K, int Nfft, const float2* __restrict__ tw, float2* __restrict__ Hout,
+                                                                   float2* __restrict__ hout, int32_t* __restrict__ index_out, int32_t* __restrict__ iters_out) {
+    __shared__ int ucol[PU_MAXK];
+    __shared__ float2 hval[PU_MAXK];
+    __shared__ int s_nu;
+    const int64_t f = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nsel = nsel_g[f] & ~TS_DONE;
+    if (tid == 0) {
+        int nu = 0;
+        for (int q = 0; q < nsel; ++q) {
+            const int c = sel_g[f * K + q];
+            int slot = -1;
+            for (int u = 0; u < nu; ++u) if (ucol[u] == c) slot = u;
+            if (slot < 0) { slot = nu; ucol[nu++] = c; }
+            hval[slot] = xs_g[f * K + q];
+        }
+        s_nu = nu;
+        if (index_out) for (int q = 0; q < K; ++q) index_out[f * K + q] = q < nsel ? sel_g[f * K + q] + 1 : 0;
+        if (iters_out) iters_out[f] = nsel;
+    }
+    __syncthreads();
+    const int nu = s_nu, Nmask = Nfft - 1;
+    if (hout) {
+        float2* hb = hout + f * (int64_t)Nfft;
+        for (int i = tid; i < Nfft; i += TS_THREADS) {
+            float2 v = make_float2(0.f, 0.f);
+            for (int u = 0; u < nu; ++u) if (ucol[u] == i) v = hval[u];
+            hb[i] = v;
+        }
+    }
+    if (Hout)
+        for (int m = tid; m < Nfft; m += TS_THREADS) {
+            float ar = 0, ai = 0;
+            for (int u = 0; u < nu; ++u) { float2 w = tw[(m * ucol[u]) & Nmask]; float2 v = hval[u]; ar += v.x * w.x - v.y * w.y; ai += v.x * w.y + v.y * w.x; }
+            Hout[f * (int64_t)Nfft + m] = make_float2(ar, ai);
+        }
+}
+
+// returns OFDM_OK and sets *handled when the tensor-core path ran
+int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, int Nfft, int K, void* H, void* h, int32_t* index, int32_t* iters,
+                bool* handled) {
+    *handled = false;
+    if (ctx->precision != OFDM_PREC_F32 || !A || K > PU_MAXK) return OFDM_OK;
+    if (getenv("OFDM_B200_NO_TC")) return OFDM_OK;
+    const char* force = getenv("OFDM_B200_FORCE_TC");
+    // a real dense contraction only: enough frames to fill 128-row tiles on every SM and a large dictionary
+    if (!force && (B < 1024 || (int64_t)Np * Ldict < (1 << 18))) return OFDM_OK;
+    if ((((uintptr_t)A) & 7) || (((uintptr_t)y) & 7)) return OFDM_OK;
+    if (!tc_get_encode()) return OFDM_OK;
+    const int K2 = ((2 * Np + TC_BK - 1) / TC_BK) * TC_BK;
+    const int Lpad = ((Ldict + 63) / 64) * 64;
+    const int64_t Bpad = ((B + TC_BM - 1) / TC_BM) * TC_BM;
+    const void* tw = ctx_twiddles(ctx, Nfft);
+    REQUIRE(ctx, tw != nullptr, "twiddle allocation failed");
+    cudaStream_t st = ctx->stream;
+    float *Bt = nullptr, *Rt = nullptr, *score = nullptr;
+    int32_t *cand = nullptr, *sel = nullptr, *nsel = nullptr, *fb = nullptr;
+    float2* xs = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&Bt, sizeof(float) * (size_t)2 * Lpad * K2, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&Rt, sizeof(float) * (size_t)Bpad * K2, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&score, sizeof(float) * (size_t)Bpad * TC_TOP, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&cand, sizeof(int32_t) * (size_t)Bpad * TC_TOP, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&sel, sizeof(int32_t) * (size_t)B * K, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&nsel, sizeof(int32_t) * (size_t)(B + 1), st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&xs, sizeof(float2) * (size_t)B * K, st));
+    fb = nsel + B;
+    CUDA_TRY(ctx, cudaMemsetAsync(fb, 0, sizeof(int32_t), st));
+    tc_dict_kernel<<<Lpad, 128, 0, st>>>((const float2*)A, Np, Ldict, K2, Bt);
+    tc_init_kernel<<<(unsigned)Bpad, 128, 0, st>>>((const float2*)y, B, Np, K2, Rt, nsel);
+    ctx->launches += 2;
+    CUtensorMap mapA, mapB;
+    int rc = OFDM_OK;
+    if (!tc_make_kmajor_map(&mapA, Rt, (uint64_t)Bpad, (uint64_t)K2) || !tc_make_kmajor_map(&mapB, Bt, (uint64_t)2 * Lpad, (uint64_t)K2))
+        rc = ctx_fail(ctx, OFDM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+    if (rc == OFDM_OK) {
+        cudaFuncSetAttribute(tc_corr_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_TOP_BYTES);
+        const size_t smem_step = sizeof(float2) * 2 * (size_t)Np;
+        cudaFuncSetAttribute(omp_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_step, 64 * 1024));
+        for (int it = 0; it < K; ++it) {
+            tc_corr_top_kernel<<<(unsigned)(Bpad / TC_BM), TC_THREADS, TC_SMEM_TOP_BYTES, st>>>(mapA, mapB, 2 * Lpad / TC_BN, K2, Ldict, cand, score);
+            omp_tc_step_kernel<<<(unsigned)B, TS_THREADS, smem_step, st>>>((const float2*)y, (const float2*)A, Np, Ldict, K2, it, cand, score, Rt, sel, nsel, xs, K, fb);
+            ctx->launches += 2;
+        }
+        omp_tc_finish_kernel<<<(unsigned)B, TS_THREADS, 0, st>>>(sel, nsel, xs, K, Nfft, (const float2*)tw, (float2*)H, (float2*)h, index, iters);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "tensor-core OMP launch failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(Bt, st); cudaFreeAsync(Rt, st); cudaFreeAsync(score, st); cudaFreeAsync(cand, st);
+    cudaFreeAsync(sel, st); cudaFreeAsync(nsel, st); cudaFreeAsync(xs, st);
+    if (rc == OFDM_OK) *handled = true;
+    return rc;
+}

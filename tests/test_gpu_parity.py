@@ -357,3 +357,38 @@ def test_ber_mer(G):
     iq = d[rng.integers(0, 16, 5000)] + 0.05 * crandn(rng, 5000)
     assert abs(G.MER_func(iq, "16QAM", precision="f64") - O.MER_func(iq, "16QAM")) < 1e-10
     assert abs(G.MER_func(iq, "16QAM") - O.MER_func(iq, "16QAM")) < 1e-4
+
+
+def test_omp_tensor_core_path_matches_simt_and_oracle(G, monkeypatch):
+    """Batched dense-dictionary OMP: tcgen05 correlation + exact re-scoring (sparse_tc.cu) must select the same
+    taps as the SIMT kernel for every frame, and as the float64 oracle on a sample of frames."""
+    rng = np.random.default_rng(41)
+    pil = np.sort(rng.permutation(1024)[:256]) + 1
+    L, Nfft, K, B = 1024, 4096, 7, 1500
+    A = O.sensing_matrix_dft(pil, Nfft, L)
+    Y = np.zeros((B, 256), dtype=complex)
+    for b in range(B):
+        h = np.zeros(Nfft, dtype=complex)
+        taps = rng.permutation(200)[:5]
+        h[taps] = crandn(rng, 5) * np.array([1, .8, .6, .4, .3])
+        Y[b] = np.fft.fft(h)[pil - 1] + 0.02 * crandn(rng, 256)
+    ctx = G.default_context("f32")
+    y_d = ctx.cplx(Y)
+    A_d = ctx.cplx(np.asfortranarray(A).ravel(order="F"))
+    monkeypatch.setenv("OFDM_B200_NO_TC", "1")
+    H0, h0, idx0, it0 = ctx.omp(y_d, Nfft, K, A_dev=A_d)
+    ctx.sync()
+    monkeypatch.delenv("OFDM_B200_NO_TC")
+    l0 = ctx.launches
+    H1, h1, idx1, it1 = ctx.omp(y_d, Nfft, K, A_dev=A_d)
+    ctx.sync()
+    assert ctx.launches - l0 == 2 + 2 * K + 1            # dictionary + init, K x (tcgen05 GEMM + step), finish
+    idx0, idx1, it0, it1 = idx0.cpu().numpy(), idx1.cpu().numpy(), it0.cpu().numpy(), it1.cpu().numpy()
+    assert np.array_equal(it0, it1)
+    assert np.mean(np.all(idx0 == idx1, axis=1)) > 0.995       # FP32 near-ties may order two taps differently
+    same = np.all(idx0 == idx1, axis=1)
+    assert rel_err(H1.cpu().numpy()[same], H0.cpu().numpy()[same]) < 1e-4
+    for b in range(0, B, 97):
+        Hr, hr, ir = O.OMP_estimate(Y[b], A, Nfft, K, 20)
+        n = int(it1[b])
+        assert list(idx1[b, :n]) == list(ir) and rel_err(H1[b].cpu().numpy(), Hr) < 2e-4
