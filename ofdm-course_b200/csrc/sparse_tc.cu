@@ -37,17 +37,37 @@ __global__ void tc_init_kernel(const float2* __restrict__ Y, int64_t B, int Np, 
     if (threadIdx.x == 0 && f < B) nsel[f] = 0;
 }
 
-// One OMP iteration for one frame.
+// sum N doubles per thread over the block (TS_THREADS = 4 warps): one pass of shuffles, two barriers
+template <int N> __device__ __forceinline__ void block_sum_vec(double (&v)[N], double* sh /* 4*N */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) sh[w * N + k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] = (sh[k] + sh[N + k]) + (sh[2 * N + k] + sh[3 * N + k]);
+    __syncthreads();
+}
+
+#define TS_MAXK 16
+// One OMP iteration for one frame.  Per-frame state lives in global memory between iterations: the selection list,
+// the coefficients, the Gram matrix of the unique selected columns and its right-hand side (both double), and the
+// residual (inside the GEMM's A operand).  The Gram matrix grows by one row per iteration.
 __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* __restrict__ Y, const float2* __restrict__ A, int Np, int Ldict, int K2, int it,
                                                                  const int32_t* __restrict__ cand, const float* __restrict__ cand_score,
                                                                  float* __restrict__ Rt, int32_t* __restrict__ sel_g, int32_t* __restrict__ nsel_g,
-                                                                 float2* __restrict__ xs_g, int K, int32_t* __restrict__ fallbacks) {
+                                                                 float2* __restrict__ xs_g, double2* __restrict__ G_g, double2* __restrict__ rhs_g, int K,
+                                                                 int32_t* __restrict__ fallbacks) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ double red[32];
+    __shared__ double shred[4 * 2 * (TS_MAXK + 2)];
     __shared__ float sval[32];
     __shared__ int sidx[32];
-    __shared__ int sel[PU_MAXK], uniq[PU_MAXK], ucol[PU_MAXK], umult[PU_MAXK];
+    __shared__ int sel[TS_MAXK], uniq[TS_MAXK], ucol[TS_MAXK], umult[TS_MAXK];
     __shared__ double2 G[PU_MAXK][PU_MAXK], Lm[PU_MAXK][PU_MAXK], grhs[PU_MAXK], xu[PU_MAXK];
+    __shared__ int s_col, s_nu, s_new;
     const int64_t f = blockIdx.x;
     const int tid = threadIdx.x;
     int nsel = nsel_g[f];
@@ -56,25 +76,34 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
     float2* yv = r + Np;
     float* row = Rt + f * K2;
     for (int i = tid; i < Np; i += TS_THREADS) { r[i] = make_float2(row[i], row[Np + i]); yv[i] = Y[f * Np + i]; }
-    for (int q = tid; q < nsel; q += TS_THREADS) sel[q] = sel_g[f * K + q];
+    if (tid < nsel) sel[tid] = sel_g[f * K + tid];
     __syncthreads();
-    // ---- exact FP32 re-scoring of the screened candidates (first maximum wins, as MATLAB's max)
-    int col;
+    // ---- exact re-scoring of the screened candidates in one pass (first maximum wins, as MATLAB's max)
     {
         const float s0 = cand_score[f * TC_TOP], s3 = cand_score[f * TC_TOP + TC_TOP - 1];
-        float best = -CUDART_INF_F; int bi = 0x7fffffff;
-        if (s3 < 0.98f * s0 && s0 > 0.f) {
-            for (int c = 0; c < TC_TOP; ++c) {
-                const int l = cand[f * TC_TOP + c];
-                const float2* a = A + (size_t)l * Np;
-                double2 acc = make_double2(0, 0);
-                for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(r[i]), to_d(a[i]));     // conj(a) * r
-                acc = block_csum(acc, red);
-                const float m = (float)(acc.x * acc.x + acc.y * acc.y);
-                if (m > best || (m == best && l < bi)) { best = m; bi = l; }
+        if (s3 < 0.995f * s0 && s0 > 0.f) {   // TF32 scores are good to ~2e-3: the exact argmax is then inside the top-4
+            int cl[TC_TOP];
+            double acc[2 * TC_TOP];
+#pragma unroll
+            for (int c = 0; c < TC_TOP; ++c) { cl[c] = cand[f * TC_TOP + c]; acc[2 * c] = 0; acc[2 * c + 1] = 0; }
+            for (int i = tid; i < Np; i += TS_THREADS) {
+                const double2 rv = to_d(r[i]);
+#pragma unroll
+                for (int c = 0; c < TC_TOP; ++c) { const double2 t = cmulc(rv, to_d(A[(size_t)cl[c] * Np + i])); acc[2 * c] += t.x; acc[2 * c + 1] += t.y; }   // conj(a) * r
+            }
+            block_sum_vec<2 * TC_TOP>(acc, shred);
+            if (tid == 0) {
+                float best = -CUDART_INF_F; int bi = 0x7fffffff;
+#pragma unroll
+                for (int c = 0; c < TC_TOP; ++c) {
+                    const float m = (float)(acc[2 * c] * acc[2 * c] + acc[2 * c + 1] * acc[2 * c + 1]);
+                    if (m > best || (m == best && cl[c] < bi)) { best = m; bi = cl[c]; }
+                }
+                s_col = (bi == 0x7fffffff) ? 0 : bi;
             }
         } else {                                        // TF32 ranking too close to call: exact search over every column
             if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1);
+            float best = -CUDART_INF_F; int bi = 0x7fffffff;
             for (int l = tid; l < Ldict; l += TS_THREADS) {
                 const float2* a = A + (size_t)l * Np;
                 float ar = 0, ai = 0;
@@ -83,60 +112,76 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
                 if (m > best) { best = m; bi = l; }
             }
             block_argmax(best, bi, sval, sidx);
+            if (tid == 0) s_col = (bi == 0x7fffffff) ? 0 : bi;
         }
-        col = (bi == 0x7fffffff) ? 0 : bi;
     }
     // ---- unique columns so far (duplicates share one unknown: pinv's minimum-norm split)
     if (tid == 0) {
-        sel[nsel] = col;
         int nu = 0;
-        for (int q = 0; q <= nsel; ++q) {
+        for (int q = 0; q < nsel; ++q) {
             int slot = -1;
             for (int u = 0; u < nu; ++u) if (ucol[u] == sel[q]) slot = u;
             if (slot < 0) { ucol[nu] = sel[q]; umult[nu] = 1; uniq[q] = nu; ++nu; } else { umult[slot] += 1; uniq[q] = slot; }
         }
-        sidx[0] = nu;
-    }
-    __syncthreads();
-    const int nu = sidx[0];
-    nsel += 1;
-    // ---- Gram matrix and right-hand side in double, x = pinv(A_sel) * y
-    for (int q = 0; q < nu; ++q)
-        for (int j = q; j < nu; ++j) {
-            const float2* aq = A + (size_t)ucol[q] * Np;
-            const float2* aj = A + (size_t)ucol[j] * Np;
-            double2 acc = make_double2(0, 0);
-            for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(aj[i]), to_d(aq[i]));       // conj(a_q) * a_j
-            acc = block_csum(acc, red);
-            if (tid == 0) { G[q][j] = acc; G[j][q] = cconj(acc); }
-        }
-    for (int q = 0; q < nu; ++q) {
-        const float2* aq = A + (size_t)ucol[q] * Np;
-        double2 acc = make_double2(0, 0);
-        for (int i = tid; i < Np; i += TS_THREADS) acc = acc + cmulc(to_d(yv[i]), to_d(aq[i]));
-        acc = block_csum(acc, red);
-        if (tid == 0) grhs[q] = acc;
     }
     __syncthreads();
     if (tid == 0) {
-        chol_solve(nu, G, grhs, xu, Lm);
+        const int col = s_col;
+        int nu = 0;
+        for (int q = 0; q < nsel; ++q) nu = max(nu, uniq[q] + 1);
+        int slot = -1;
+        for (int u = 0; u < nu; ++u) if (ucol[u] == col) slot = u;
+        sel[nsel] = col;
+        if (slot < 0) { ucol[nu] = col; umult[nu] = 1; uniq[nsel] = nu; s_new = 1; ++nu; } else { umult[slot] += 1; uniq[nsel] = slot; s_new = 0; }
+        s_nu = nu;
+    }
+    __syncthreads();
+    const int nu = s_nu, col = s_col;
+    nsel += 1;
+    double2* Gf = G_g + f * (int64_t)K * K;
+    double2* rf = rhs_g + f * (int64_t)K;
+    // ---- the Gram matrix grows by one row (new unique column only): nu dots + the right-hand side, one reduction
+    if (s_new) {
+        double acc[2 * (TS_MAXK + 1)];
+#pragma unroll
+        for (int k = 0; k < 2 * (TS_MAXK + 1); ++k) acc[k] = 0;
+        const float2* an = A + (size_t)col * Np;
+        for (int i = tid; i < Np; i += TS_THREADS) {
+            const double2 av = to_d(an[i]);
+#pragma unroll
+            for (int q = 0; q < TS_MAXK; ++q)
+                if (q < nu) { const double2 t = cmulc(av, to_d(A[(size_t)ucol[q] * Np + i])); acc[2 * q] += t.x; acc[2 * q + 1] += t.y; }   // conj(a_q) * a_new
+            const double2 t = cmulc(to_d(yv[i]), av);                                                                                  // conj(a_new) * y
+            acc[2 * TS_MAXK] += t.x; acc[2 * TS_MAXK + 1] += t.y;
+        }
+        block_sum_vec<2 * (TS_MAXK + 1)>(acc, shred);
+        if (tid == 0) {
+            for (int q = 0; q < nu; ++q) Gf[q * K + (nu - 1)] = make_double2(acc[2 * q], acc[2 * q + 1]);
+            rf[nu - 1] = make_double2(acc[2 * TS_MAXK], acc[2 * TS_MAXK + 1]);
+        }
+        __syncthreads();
+    }
+    if (tid < nu * nu) { const int q = tid / nu, j = tid % nu; G[q][j] = (q <= j) ? Gf[q * K + j] : cconj(Gf[j * K + q]); }
+    if (tid < nu) grhs[tid] = rf[tid];
+    __syncthreads();
+    if (tid == 0) {
+        chol_solve(nu, G, grhs, xu, Lm);                // x = pinv(A_sel) * y on the unique columns
         for (int q = 0; q < nsel; ++q) { double2 v = cscale(xu[uniq[q]], 1.0 / (double)umult[uniq[q]]); xs_g[f * K + q] = make_float2((float)v.x, (float)v.y); }
         sel_g[f * K + nsel - 1] = col;
     }
     __syncthreads();
     // ---- residue = y - A*x and the stopping rule (`OMP_estimate.m:18-22`)
-    double dn = 0, on = 0;
+    double nrm[2] = {0, 0};
     for (int i = tid; i < Np; i += TS_THREADS) {
         double2 acc = to_d(yv[i]);
         for (int q = 0; q < nu; ++q) acc = acc - cmul(to_d(A[(size_t)ucol[q] * Np + i]), xu[q]);
         const double2 old = to_d(r[i]);
-        dn += (acc.x - old.x) * (acc.x - old.x) + (acc.y - old.y) * (acc.y - old.y);
-        on += old.x * old.x + old.y * old.y;
+        nrm[0] += (acc.x - old.x) * (acc.x - old.x) + (acc.y - old.y) * (acc.y - old.y);
+        nrm[1] += old.x * old.x + old.y * old.y;
         row[i] = (float)acc.x; row[Np + i] = (float)acc.y;
     }
-    dn = block_sum(dn, red);
-    on = block_sum(on, red);
-    if (tid == 0) nsel_g[f] = nsel | ((it >= 1 && sqrt(dn) / sqrt(on) < 1e-2) ? TS_DONE : 0);
+    block_sum_vec<2>(nrm, shred);
+    if (tid == 0) nsel_g[f] = nsel | ((it >= 1 && sqrt(nrm[0]) / sqrt(nrm[1]) < 1e-2) ? TS_DONE : 0);
 }
 
 // h(index(i1)) = x(i1) in selection order (later duplicates overwrite), H = fft(h) as a K-term sum
@@ -184,7 +229,7 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_finish_kernel(const int32_t
 int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, int Nfft, int K, void* H, void* h, int32_t* index, int32_t* iters,
                 bool* handled) {
     *handled = false;
-    if (ctx->precision != OFDM_PREC_F32 || !A || K > PU_MAXK) return OFDM_OK;
+    if (ctx->precision != OFDM_PREC_F32 || !A || K > TS_MAXK) return OFDM_OK;
     if (getenv("OFDM_B200_NO_TC")) return OFDM_OK;
     const char* force = getenv("OFDM_B200_FORCE_TC");
     // a real dense contraction only: enough frames to fill 128-row tiles on every SM and a large dictionary
@@ -200,6 +245,7 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
     float *Bt = nullptr, *Rt = nullptr, *score = nullptr;
     int32_t *cand = nullptr, *sel = nullptr, *nsel = nullptr, *fb = nullptr;
     float2* xs = nullptr;
+    double2 *Gs = nullptr, *rhs = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync((void**)&Bt, sizeof(float) * (size_t)2 * Lpad * K2, st));
     CUDA_TRY(ctx, cudaMallocAsync((void**)&Rt, sizeof(float) * (size_t)Bpad * K2, st));
     CUDA_TRY(ctx, cudaMallocAsync((void**)&score, sizeof(float) * (size_t)Bpad * TC_TOP, st));
@@ -207,6 +253,8 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
     CUDA_TRY(ctx, cudaMallocAsync((void**)&sel, sizeof(int32_t) * (size_t)B * K, st));
     CUDA_TRY(ctx, cudaMallocAsync((void**)&nsel, sizeof(int32_t) * (size_t)(B + 1), st));
     CUDA_TRY(ctx, cudaMallocAsync((void**)&xs, sizeof(float2) * (size_t)B * K, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&Gs, sizeof(double2) * (size_t)B * K * K, st));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&rhs, sizeof(double2) * (size_t)B * K, st));
     fb = nsel + B;
     CUDA_TRY(ctx, cudaMemsetAsync(fb, 0, sizeof(int32_t), st));
     tc_dict_kernel<<<Lpad, 128, 0, st>>>((const float2*)A, Np, Ldict, K2, Bt);
@@ -222,7 +270,7 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
         cudaFuncSetAttribute(omp_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_step, 64 * 1024));
         for (int it = 0; it < K; ++it) {
             tc_corr_top_kernel<<<(unsigned)(Bpad / TC_BM), TC_THREADS, TC_SMEM_TOP_BYTES, st>>>(mapA, mapB, 2 * Lpad / TC_BN, K2, Ldict, cand, score);
-            omp_tc_step_kernel<<<(unsigned)B, TS_THREADS, smem_step, st>>>((const float2*)y, (const float2*)A, Np, Ldict, K2, it, cand, score, Rt, sel, nsel, xs, K, fb);
+            omp_tc_step_kernel<<<(unsigned)B, TS_THREADS, smem_step, st>>>((const float2*)y, (const float2*)A, Np, Ldict, K2, it, cand, score, Rt, sel, nsel, xs, Gs, rhs, K, fb);
             ctx->launches += 2;
         }
         omp_tc_finish_kernel<<<(unsigned)B, TS_THREADS, 0, st>>>(sel, nsel, xs, K, Nfft, (const float2*)tw, (float2*)H, (float2*)h, index, iters);
@@ -231,7 +279,7 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
         if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "tensor-core OMP launch failed: %s", cudaGetErrorString(e));
     }
     cudaFreeAsync(Bt, st); cudaFreeAsync(Rt, st); cudaFreeAsync(score, st); cudaFreeAsync(cand, st);
-    cudaFreeAsync(sel, st); cudaFreeAsync(nsel, st); cudaFreeAsync(xs, st);
+    cudaFreeAsync(sel, st); cudaFreeAsync(nsel, st); cudaFreeAsync(xs, st); cudaFreeAsync(Gs, st); cudaFreeAsync(rhs, st);
     if (rc == OFDM_OK) *handled = true;
     return rc;
 }
