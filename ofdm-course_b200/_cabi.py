@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libofdm_b200.so")
+# OFDM_B200_LIB selects another build of the same library (kernel A/B experiments, tools/ab_variants.sh)
+LIB_PATH = os.environ.get("OFDM_B200_LIB") or os.path.join(_HERE, "lib", "libofdm_b200.so")
 
 vp, i32, i64, u64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 pi32 = C.POINTER(C.c_int32)

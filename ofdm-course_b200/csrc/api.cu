@@ -279,7 +279,9 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
     const int nk = (int)x.size();
     p.n_knots = nk;
     const bool spline = (method == OFDM_INTERP_SPLINE);
-    const double tol = (ctx->precision == OFDM_PREC_F64) ? 1e-19 : 1e-10;
+    // entries of the derivative operator below tol * max are dropped (they decay like 0.268^distance): 1e-8 is
+    // below half an FP32 ulp of the result, 1e-19 below a double's
+    const double tol = (ctx->precision == OFDM_PREC_F64) ? 1e-19 : 1e-8;
 
     // derivative operator, column by column, kept as [lo,hi] ranges above the threshold
     std::vector<std::vector<long double>> cols;

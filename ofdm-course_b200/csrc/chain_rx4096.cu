@@ -13,8 +13,8 @@
 #include "interp.cuh"
 
 #define FX_THREADS 256
-#define XROW 257          // pass-B output row stride (k1): +1 pad makes pass C's reads bank-conflict free with immediate offsets
-#define XBUF 4112         // samples per symbol buffer: 15*257 + 255 + 1, rounded to 16
+#define XROW 258          // pass-B output row stride (k1): +2 pad keeps rows 16-byte aligned and makes pass C's 128-bit reads conflict free
+#define XBUF 4128         // samples per symbol buffer: 15*258 + 256, rounded to 16
 #define SLOT_ZERO (-2147483647 - 1)
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
@@ -25,6 +25,17 @@ __device__ __forceinline__ float2 ld_stream(const float2* p) {   // streaming lo
     asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
+
+// Cache policy: the symbol stream goes through the copy engine and never touches L1, so what is left of L1 beside
+// 2 x 89 KB of shared memory (~55 KB) can hold the channel-estimate tables that every stream re-reads -- provided
+// the one-shot traffic (reference bits in, decided bits and H out) does not allocate there.
+__device__ __forceinline__ uint32_t ldg_once(const uint32_t* p) {
+    uint32_t r;
+    asm("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_once(uint32_t* p, uint32_t v) { asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void stg_once(float2* p, float2 v) { asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
 
 // Packed FP32x2 arithmetic (FADD2 / FFMA2, new on sm_100): one issue slot per complex add.  Measured on
 // B200 (tools/ubench_fp32x2.cu): FADD2 127, FFMA2 117, scalar FADD 117, scalar 3-register FFMA 71
@@ -70,7 +81,7 @@ struct Fast4096Params {
     const int32_t* slot;       // 1024 entries for carriers 0..1023 (data rank / -1-pilot / SLOT_ZERO)
     const float2* pilots;      // Np (first symbol column)
     const float2* tw4096;      // W4096^k
-    float inv_sqrt10;
+    float inv_sqrt10, two_a;   // 16QAM level unit a = 1/sqrt(10) and the inner decision boundary 2a
 };
 
 // 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`).
@@ -123,8 +134,9 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // prefetched two items ahead into a two-buffer ring by one elected thread; all three FFT passes run
 // in place in the buffer the symbol landed in:
 //   pass A  x[256 n1 + t]            -> same places, index k1 replaces n1          (thread-private)
-//   pass B  [256 k1 + 16 n2 + n3]    -> [257 k1 + 16 k2 + n3]                        (row pad of one sample)
-//   pass C  reads 16 consecutive n3 per (k1,k2) with immediate offsets: conflict-free because of the pad.
+//   pass B  [256 k1 + 16 n2 + n3]    -> [258 k1 + 16 k2 + n3]                        (row pad of two samples)
+//   pass C  reads 16 consecutive n3 per (k1,k2) as eight 128-bit loads with immediate offsets: conflict-free
+//           because of the pad (129 k1 mod 8 is a permutation over a quarter warp).
 template <bool QAM16, bool NEAR, int LOADMODE>
 __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
@@ -155,7 +167,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     }
     const int symlen = 4096 + p.Tg;
     const int64_t stream_words = (int64_t)p.frame_words * p.frames;
-    const float two_a = 2.f * p.inv_sqrt10;
+    const float two_a = p.two_a;
     const int64_t my_streams = (B - blockIdx.x + gridDim.x - 1) / gridDim.x;
     const int64_t n_items = my_streams * p.S;
     const int64_t stream_stride = (int64_t)p.S * symlen;                 // samples per stream
@@ -197,6 +209,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     int cur_s = 0;
     int errs = 0, nears = 0;
     int s = 0, sf = 0, f = 0;
+    int sfNd = 0;                                  // sf * Nd: row of the frame's decision buffer this symbol fills
     int64_t b = blockIdx.x;
     uint32_t parity = 0;
     for (int64_t q = 0; q < n_items; ++q) {
@@ -247,9 +260,13 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         __syncthreads();
         // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
         {
-            const float2* rp = X + (tid & 15) * XROW + (tid >> 4) * 16;
+            const float4* rp = reinterpret_cast<const float4*>(X + (tid & 15) * XROW + (tid >> 4) * 16);
 #pragma unroll
-            for (int n3 = 0; n3 < 16; ++n3) v[n3] = rp[n3];
+            for (int j = 0; j < 8; ++j) {
+                const float4 w = rp[j];
+                v[2 * j] = make_float2(w.x, w.y);
+                v[2 * j + 1] = make_float2(w.z, w.w);
+            }
         }
         __syncthreads();                           // buffer `cur` is free: refill it with item q+2
         if (tid == 0) {
@@ -266,7 +283,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         if (sf == p.SpF - 1 && txbits) {           // reference words of this frame, consumed ~400 instructions later
             const uint32_t* tp = txbits + b * stream_words + (int64_t)f * p.frame_words + tid;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = __ldg(tp + FX_THREADS * j);
+            for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = ldg_once(tp + FX_THREADS * j);
         }
         fft16_steps12(v);
         float2 Y[4];
@@ -284,7 +301,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             __syncthreads();
             for (int k = tid; k < p.Nc; k += FX_THREADS) {
                 float2 h = Hinv[k];
-                if (Hout) Hout[b * p.Nc + k] = h;
+                if (Hout) stg_once(Hout + b * p.Nc + k, h);
                 float dd = h.x * h.x + h.y * h.y;
                 Hinv[k] = make_float2(h.x / dd, -h.y / dd);
             }
@@ -292,7 +309,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         }
         // ---- equalise + decide (branch-free per carrier; pilots / unused carriers skip the store)
         {
-            uint8_t* sp = symidx + sf * p.Nd;
+            uint8_t* sp = symidx + sfNd;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const uint32_t dr = ((c < 2 ? role01 : role23) >> (16 * (c & 1))) & 0xFFFFu;
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                         o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
                     }
                     if (txbits) errs += __popc(o ^ txw[j]);
-                    if (outbits) outbits[wbase + w] = o;
+                    if (outbits) stg_once(outbits + wbase + w, o);
                 }
             }
             for (int w = tid + 4 * FX_THREADS; w < p.frame_words; w += FX_THREADS) {   // frames longer than 32 Kbit
@@ -351,7 +368,8 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 if (outbits) outbits[wbase + w] = o;
             }
         }
-        if (++sf == p.SpF) { sf = 0; ++f; }
+        sfNd += p.Nd;
+        if (++sf == p.SpF) { sf = 0; sfNd = 0; ++f; }
         if (++s == p.S) {   // stream complete: one atomic per warp that saw errors, no block barrier
             const int we = warp_sum(errs);
             if ((tid & 31) == 0 && we) {
@@ -363,7 +381,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 if ((tid & 31) == 0 && wn && counts) atomicAdd(&counts[2], (unsigned long long)wn);
             }
             if (tid == 0 && counts) atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
-            errs = 0; nears = 0; s = 0; sf = 0; f = 0;
+            errs = 0; nears = 0; s = 0; sf = 0; sfNd = 0; f = 0;
             b += gridDim.x;
         }
     }
@@ -395,6 +413,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, lp->Np);
     p.tw4096 = (const float2*)ctx_twiddles(ctx, 4096);
     p.inv_sqrt10 = (float)ct.re[12];   // +1/sqrt(10) with the table's own normalisation
+    p.two_a = 2.f * p.inv_sqrt10;
     REQUIRE(ctx, p.slot && p.pilots && p.tw4096, "device upload failed");
     if (lp->Tg & 1) return OFDM_OK;          // bulk copies need 16-byte aligned symbol starts
     if (((uintptr_t)rx) & 15) return OFDM_OK;

@@ -40,7 +40,25 @@ __device__ __forceinline__ void plan_apply_fn(const PlanDev<T>& p, cx<T>* y, cx<
     }
     const int bw = 2 * p.hb + 1;
     const int jlo = p.folded ? p.ext_lo : 0, jhi = p.folded ? n - p.ext_hi : n;   // columns the operator may read
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    // A few rows beyond a multiple of the block size (n = Np + 2 = 258 with 256 threads) would make two threads
+    // walk a second row while everybody else waits at the barrier: give each of them to a warp, one lane per tap.
+    int n_rows = n;
+    {
+        const int left = n % (int)blockDim.x, nw = (int)blockDim.x >> 5;
+        if (p.hb > 0 && n > (int)blockDim.x && left > 0 && left <= nw) {
+            n_rows = n - left;
+            const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            if (w < left) {
+                const int i = n_rows + w;
+                const int c0 = max(0, p.hb - i + jlo), c1 = min(bw, jhi - i + p.hb);
+                T ar = 0, ai = 0;
+                for (int c = c0 + lane; c < c1; c += 32) { T wt = p.band[(size_t)c * n + i]; C v = y[i - p.hb + c]; ar += wt * v.x; ai += wt * v.y; }
+                ar = warp_sum(ar); ai = warp_sum(ai);
+                if (lane == 0) d[i] = mk<T>(ar, ai);
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < n_rows; i += blockDim.x) {
         T ar = 0, ai = 0;
         if (p.hb > 0) {
             const T* col = p.band + i;            // band is stored tap-major [bw][n]: coalesced across threads
