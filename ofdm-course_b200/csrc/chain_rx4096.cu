@@ -11,6 +11,7 @@
 //   W4096^{nk} = W16^{n1k1} * W4096^{(16n2+n3)k1} * W16^{n2k2} * W256^{n3k2} * W16^{n3k3}.
 // Only outputs k < 1024 are needed, so pass C evaluates 4 of its 16 outputs.
 #include "interp.cuh"
+#include "fft_reg.cuh"
 
 #define FX_THREADS 256
 #define XROW 258          // pass-B output row stride (k1): +2 pad keeps rows 16-byte aligned and makes pass C's 128-bit reads conflict free
@@ -37,44 +38,6 @@ __device__ __forceinline__ uint32_t ldg_once(const uint32_t* p) {
 __device__ __forceinline__ void stg_once(uint32_t* p, uint32_t v) { asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void stg_once(float2* p, float2 v) { asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
 
-// Packed FP32x2 arithmetic (FADD2 / FFMA2, new on sm_100): one issue slot per complex add.  Measured on
-// B200 (tools/ubench_fp32x2.cu): FADD2 127, FFMA2 117, scalar FADD 117, scalar 3-register FFMA 71
-// results/clk/SM -- the packed forms halve the issue slots of the butterflies.
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
-__device__ __forceinline__ void fft4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    const float2 t0 = add2(a0, a2), t1 = sub2(a0, a2), t2 = add2(a1, a3);
-    const float2 t3s = make_float2(a1.y - a3.y, a1.x - a3.x);          // (a1 - a3) with the halves swapped
-    a0 = add2(t0, t2);
-    a2 = sub2(t0, t2);
-    a1 = __ffma2_rn(t3s, make_float2(1.f, -1.f), t1);                   // t1 + (-i)(a1 - a3)
-    a3 = __ffma2_rn(t3s, make_float2(-1.f, 1.f), t1);                   // t1 - (-i)(a1 - a3)
-}
-#define C16_1 0.92387953251128674f
-#define S16_1 0.38268343236508977f
-#define RSQ2 0.70710678118654752f
-// v[4a+b] in  ->  X[c+4d] at v[4c+d]   (forward 16-point DFT, radix 4x4)
-__device__ __forceinline__ void fft16_steps12(float2* v) {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) fft4(v[b], v[4 + b], v[8 + b], v[12 + b]);
-    // y_b[c] sits at v[4c+b]; multiply by W16^{bc}
-    float2 t;
-    t = v[5];  v[5]  = make_float2(t.x * C16_1 + t.y * S16_1, t.y * C16_1 - t.x * S16_1);       // W16^1
-    t = v[6];  v[6]  = make_float2((t.x + t.y) * RSQ2, (t.y - t.x) * RSQ2);                       // W16^2
-    t = v[7];  v[7]  = make_float2(t.x * S16_1 + t.y * C16_1, t.y * S16_1 - t.x * C16_1);       // W16^3
-    t = v[9];  v[9]  = make_float2((t.x + t.y) * RSQ2, (t.y - t.x) * RSQ2);                       // W16^2
-    t = v[10]; v[10] = make_float2(t.y, -t.x);                                                      // W16^4 = -i
-    t = v[11]; v[11] = make_float2((t.y - t.x) * RSQ2, -(t.x + t.y) * RSQ2);                      // W16^6
-    t = v[13]; v[13] = make_float2(t.x * S16_1 + t.y * C16_1, t.y * S16_1 - t.x * C16_1);       // W16^3
-    t = v[14]; v[14] = make_float2((t.y - t.x) * RSQ2, -(t.x + t.y) * RSQ2);                      // W16^6
-    t = v[15]; v[15] = make_float2(-t.x * C16_1 - t.y * S16_1, t.x * S16_1 - t.y * C16_1);      // W16^9
-}
-__device__ __forceinline__ void fft16(float2* v) {
-    fft16_steps12(v);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) fft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-}
-
 struct Fast4096Params {
     int Tg, S, SpF, Nc, Nd, Np, frame_words, frames, scramble, con_id;
     uint32_t prev0;
@@ -83,23 +46,6 @@ struct Fast4096Params {
     const float2* tw4096;      // W4096^k
     float inv_sqrt10, two_a;   // 16QAM level unit a = 1/sqrt(10) and the inner decision boundary 2a
 };
-
-// 16QAM hard decision, separable, with the reference's first-minimum tie rule (`demapping.m:12`).
-// Table index = 8*(x>0) + 4*(|x|<2a) + 2*(y<0) + (|y|<2a): I levels {-3,-1,+3,+1} -> codes {00,01,10,11},
-// Q levels {+3,+1,-3,-1} -> {00,01,10,11}; ties (x = 0, |x| = 2a, ...) fall to the lower table index
-// exactly as `min` does, and a NaN never wins a '<' so it decodes to index 1 (bits 0000).
-// Returned value is the index bit-reversed (MSB-first symbol bits inside LSB-first packing).
-template <bool NEAR>
-__device__ __forceinline__ uint32_t demap16_nib(float x, float y, float two_a, float* margin) {
-    const float ax = fabsf(x), ay = fabsf(y);
-    uint32_t nib = (x > 0.f ? 1u : 0u) | (ax < two_a ? 2u : 0u) | (y < 0.f ? 4u : 0u) | (ay < two_a ? 8u : 0u);
-    if (!(ax + ay <= CUDART_INF_F)) nib = 0u;                             // NaN in either part
-    if (NEAR) {
-        float dx = fminf(ax, fabsf(ax - two_a)), dy = fminf(ay, fabsf(ay - two_a));
-        *margin = 2.f * two_a * fminf(dx, dy);  // second-best minus best squared distance
-    }
-    return nib;
-}
 
 // ---- mbarrier / bulk-copy (TMA) helpers --------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

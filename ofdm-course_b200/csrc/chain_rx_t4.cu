@@ -10,6 +10,7 @@
 // FFT phase and the decision phase, because fine_sync's estimates need all symbols before any of them is corrected.
 #include "fft.cuh"
 #include "interp.cuh"
+#include "fft_reg.cuh"
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
 uint32_t ofdm_reg_to_prev(const uint8_t* reg);
@@ -238,6 +239,289 @@ __global__ void __launch_bounds__(T4_THREADS) rx_t4_kernel(T4Params p, PlanDev<f
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fast path for Nfft = 1024 (the Task-4 shape): same chain, same order of operations, but
+//   * a symbol is transformed by ONE WARP: 1024 = 32 x 32, lane n2 runs a register-resident 32-point DFT over
+//     n1 (x[32 n1 + n2], coalesced 256-byte rows straight from global memory, all 32 loads in flight), the
+//     W1024^{n2 k1} twiddles come from a transposed table (L1-resident), a 32 x 33 warp-private shared tile does
+//     the transpose, lane k1 runs the second 32-point DFT over n2 and keeps bins k1 + 32 k2 -- only k2 < K2N
+//     (N_carrier <= 32 K2N) are ever produced, the rest is pruned at compile time.  No block barrier inside the
+//     symbol loop: the eight warps of a CTA work on eight symbols of the stream at once.
+//   * the per-symbol base rotation of the CFO/IFO removal is applied to the kept bins (the DFT is linear), the
+//     per-sample part exp(-2j*pi*c*i/Nfft) comes from a per-stream shared table;
+//   * 16QAM decisions use the separable rule and the frame's bits are packed eight symbols per word.
+// Estimators (fine_sync) and the channel estimate are the code of the generic kernel above.
+#define T4F_EROW 33
+__device__ __forceinline__ float2 ldg_stream(const float2* p) {   // the sample stream is read once here: keep it out of L1 (tables live there)
+    float2 r;
+    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+struct T4FastExtra {
+    const float2* tw_t;        // [k1][n2] = W1024^{n2*k1}: transposed twiddles, coalesced across lanes
+    float two_a;
+};
+
+template <int K2N, bool QAM16, bool NEAR>
+__global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T4FastExtra fx, PlanDev<float> plan, DevConst<float> con,
+                                                                    const float2* __restrict__ rx, int64_t B, int64_t L,
+                                                                    const int32_t* __restrict__ tg_pos, const double* __restrict__ freq_off,
+                                                                    float2* __restrict__ scratch, const uint32_t* __restrict__ txbits, int64_t total_bits,
+                                                                    uint32_t* __restrict__ outbits, unsigned long long* __restrict__ counts,
+                                                                    int32_t* __restrict__ ifo_out, double* __restrict__ tau_out,
+                                                                    double* __restrict__ phase_out, float2* __restrict__ Hout, float near_eps) {
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int red_i[32];
+    __shared__ int cnt[T4_THREADS];
+    __shared__ int ifo_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T4_THREADS / 32;
+    const int M = p.Np * p.S;
+    // layout: [phase-1 tiles | phase-2 taus] (aliased) , wtab, Yp, rot_s, G, yk, dk, raw, symidx
+    const size_t tiles_bytes = sizeof(float2) * (size_t)NW * 32 * T4F_EROW;
+    const size_t taus_bytes = sizeof(double) * (size_t)M;
+    float2* tiles = (float2*)smem_raw;
+    double* taus = (double*)smem_raw;
+    float2* wtab = (float2*)(smem_raw + ((tiles_bytes > taus_bytes ? tiles_bytes : taus_bytes) + 15) / 16 * 16);
+    float2* Yp = wtab + N;                           // pilots of every symbol, [s][p]
+    float2* rot_s = Yp + M;                          // per-symbol base rotation
+    float2* G = rot_s + p.S;                         // per-carrier correction / equaliser, Nc
+    float2* yk = G + p.Nc;
+    float2* dk = yk + plan.n_knots;
+    uint32_t* raw = (uint32_t*)(dk + plan.n_knots);
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint8_t* symidx = (uint8_t*)(((uintptr_t)(raw + fw) + 7) & ~(uintptr_t)7);   // SpF * Nd decisions, 8-byte aligned for the word-wise packer (+ slack)
+    float2* E = tiles + warp * 32 * T4F_EROW;        // this warp's transpose tile
+    const int SL = N + p.Tg;
+    float2* Ysc = scratch + (int64_t)blockIdx.x * p.S * p.Nc;   // this CTA's parking area (stays in L2)
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+
+    // one symbol-sized window starting at stream sample n0 (after the two add_STO calls): DFT bins k < 32*KK
+    // X[lane + 32 k2] are returned in v[k2]; `derot` multiplies sample i by wtab[i] first.
+    auto load_window = [&](const float2* r, int64_t n0, int tg, bool tshift, float2* v) {
+        // sample n of the corrected stream is r[n - SL + tg] for n >= SL inside the record, else 0 (`add_STO.m:5-9`)
+        const int64_t m0 = tshift ? n0 - SL + tg : n0;
+        const bool all_in = (m0 >= 0 && m0 + N <= L && (!tshift || n0 >= SL));
+        if (all_in) {
+            const float2* q = r + m0 + lane;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) v[n1] = ldg_stream(q + 32 * n1);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; ++n1) {
+                const int64_t m = m0 + 32 * n1 + lane;
+                const bool ok = m >= 0 && m < L && (!tshift || n0 + 32 * n1 + lane >= SL);
+                v[n1] = ok ? ldg_stream(r + m) : make_float2(0.f, 0.f);
+            }
+        }
+    };
+    auto pass_a = [&](float2* v) {      // DFT over n1, twiddle, transpose through the tile
+        fft32<32>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; ++k1) {
+            float2 x = v[k1];
+            if (k1) x = cmul(x, __ldg(fx.tw_t + 32 * k1 + lane));
+            E[k1 * T4F_EROW + lane] = x;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) v[n2] = E[lane * T4F_EROW + n2];
+        __syncwarp();
+    };
+
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+        const float2* r = rx + b * L;
+        const int tg = p.time_desync ? tg_pos[b] : 0;
+        const double fo = p.freq_desync ? freq_off[b] : 0.0;
+        const bool tshift = p.time_desync != 0;
+        // ---- remove_IFO: first bin of |fft(y3(Nfft+1:2*Nfft))| above 0.77 (`remove_IFO.m:5-8`), warp 0
+        int ifo = 0;
+        if (p.freq_desync) {
+            if (warp == 0) {
+                float2 v[32];
+                load_window(r, (int64_t)N, tg, tshift, v);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], rot_from_cycles(fo * (double)(N + 32 * n1 + lane) / N));
+                pass_a(v);
+                fft32<32>(v);
+                int first = 0x7fffffff;
+#pragma unroll
+                for (int k2 = 31; k2 >= 0; --k2) {
+                    const double re = v[k2].x, im = v[k2].y;
+                    if (sqrt(re * re + im * im) > 0.77) first = lane + 32 * k2;
+                }
+                first = warp_min(first);
+                if (lane == 0) ifo_s = (first == 0x7fffffff) ? -1 : first;
+            }
+            __syncthreads();
+            ifo = ifo_s;
+        }
+        if (tid == 0 && ifo_out) ifo_out[b] = ifo;
+        const double c = fo + (ifo > 0 ? ifo : 0);   // total derotation in cycles per Nfft samples
+        if (p.freq_desync) {
+            for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(c * (double)i / N);
+            for (int s = tid; s < p.S; s += T4_THREADS) rot_s[s] = rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / N);
+        }
+        __syncthreads();
+        // ---- OFDM_demodulator, one warp per symbol; park the useful bins (rotated), keep the pilots
+        for (int s = warp; s < p.S; s += NW) {
+            float2 v[32];
+            load_window(r, (int64_t)s * SL + p.Tg, tg, tshift, v);
+            if (p.freq_desync) {
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], wtab[32 * n1 + lane]);
+            }
+            pass_a(v);
+            fft32<K2N>(v);
+            const float2 rs = p.freq_desync ? rot_s[s] : make_float2(1.f, 0.f);
+#pragma unroll
+            for (int k2 = 0; k2 < K2N; ++k2) {
+                const int k = lane + 32 * k2;
+                const float2 y = p.freq_desync ? cmul(v[k2], rs) : v[k2];
+                E[k] = y;                                                  // natural order, for the pilot gather below
+                if (k < p.Nc) Ysc[(int64_t)s * p.Nc + k] = y;
+            }
+            __syncwarp();
+            for (int q = lane; q < p.Np; q += 32) Yp[s * p.Np + q] = E[p.pil0[q]];
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- fine_sync estimators (`Task 4/fine_sync.m:25-35,47-52`), in double
+        double tau = 0.0, phase = 0.0;
+        if (p.time_desync || p.freq_desync) {
+            const double deltak = (double)(p.pil0[1] - p.pil0[0]);
+            auto q_at = [&](int i) -> double2 { return cmulc(p.pilots_d[i], to_d(Yp[i])); };   // tx * conj(rx), flat column-major index
+            auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return atan2(d.y, d.x) / (2.0 * CUDART_PI * deltak); };
+            const int n = M - 1;
+            for (int j = tid; j < n; j += T4_THREADS) taus[j] = tau_at(j);                  // taus(j+1) of the reference (:25-30)
+            __syncthreads();
+            // mask = [false, abs(diffs)<1e-3 & abs(diffs)~=0]; taus_result = taus(mask); mean(taus_result(Np+1:end))  (:32-35)
+            const int CH = (n + T4_THREADS - 1) / T4_THREADS;
+            const int lo = min(tid * CH, n), hi = min(lo + CH, n);
+            int cmask = 0;
+            for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
+            cnt[tid] = cmask;
+            __syncthreads();
+            int rank = 0;
+            for (int k = 0; k < tid; ++k) rank += cnt[k];
+            double sum = 0; int kept = 0;
+            for (int j = max(lo, 1); j < hi; ++j) {
+                double d = fabs(taus[j] - taus[j - 1]);
+                if (d < 1e-3 && d != 0.0) { if (rank >= p.Np) { sum += taus[j]; ++kept; } ++rank; }
+            }
+            sum = block_sum(sum, red);
+            double nk = block_sum((double)kept, red);
+            tau = sum / nk;
+            double ps = 0; int pn = 0;
+            for (int i = tid; i < M; i += T4_THREADS) {
+                const int pq = i % p.Np;
+                double2 rxv = to_d(Yp[i]);
+                if (p.time_desync) { double sn, cs; sincospi(2.0 * tau * (double)p.pil0[pq], &sn, &cs); rxv = cmul(rxv, make_double2(cs, sn)); }
+                double2 qq = cmulc(p.pilots_d[i], rxv);
+                double a = atan2(qq.y, qq.x);
+                if (fabs(a) > 1e-3) { ps += a; ++pn; }
+            }
+            ps = block_sum(ps, red);
+            double pk = block_sum((double)pn, red);
+            phase = ps / pk;
+            if (tid == 0) { if (tau_out) tau_out[b] = tau; if (phase_out) phase_out[b] = phase; }
+        }
+        // ---- per-carrier correction factor exp(j*(2*pi*tau*k*[time] + phase*[freq])) (`fine_sync.m:38-58`)
+        for (int k = tid; k < p.Nc; k += T4_THREADS) {
+            double sn = 0.0, cs = 1.0;
+            if (p.time_desync || p.freq_desync) {
+                double ang = (p.time_desync ? 2.0 * tau * (double)k : 0.0);     // in units of pi
+                double s1, c1, s2 = 0.0, c2 = 1.0;
+                sincospi(ang, &s1, &c1);
+                if (p.freq_desync) sincos(phase, &s2, &c2);
+                cs = c1 * c2 - s1 * s2; sn = s1 * c2 + c1 * s2;
+            }
+            G[k] = make_float2((float)cs, (float)sn);
+        }
+        __syncthreads();
+        // ---- estimate_channel on the corrected grid + equalize_signal (`estimate_channel.m:4-8`)
+        if (p.mp_desync) {
+            for (int q = tid; q < p.Np; q += T4_THREADS) {
+                float sr = 0.f, si = 0.f;
+                const float2 g = G[p.pil0[q]];
+                for (int s = 0; s < p.S; ++s) { float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
+                yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
+            }
+            __syncthreads();
+            float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
+            plan_apply_fn<float>(plan, yk, dk, [&](int k, float2 h) {
+                if (Hrow) Hrow[k] = h;
+                G[k] = cdiv(G[k], h);            // equalised = Y * cf / H
+            });
+            __syncthreads();
+        }
+        // ---- get_payload, demapping, DeScrambler, BER: one frame (SpF symbols) per round
+        int errs = 0, nears = 0;
+        for (int f = 0; f < p.frames; ++f) {
+            for (int sf = 0; sf < p.SpF; ++sf) {
+                const float2* Ys = Ysc + (int64_t)(f * p.SpF + sf) * p.Nc;
+                uint8_t* sp = symidx + sf * p.Nd;
+                for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
+                    const int cidx = p.data0[dr];
+                    const float2 e = (cidx < p.Nc) ? cmul(Ys[cidx], G[cidx]) : make_float2(0.f, 0.f);
+                    float margin = 1.f;
+                    uint32_t code;
+                    if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
+                    else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                    if (NEAR && margin < near_eps) ++nears;
+                    sp[dr] = (uint8_t)code;
+                }
+            }
+            __syncthreads();
+            for (int wd = tid; wd < fw; wd += T4_THREADS) {
+                uint32_t word = 0;
+                if (QAM16) {
+                    const uint2 by = *reinterpret_cast<const uint2*>(symidx + 8 * wd);   // 8 ready-made nibbles, one per byte
+                    uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
+                    uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
+                    word = lo | (hi << 16);
+                    const int nb = p.frame_bits - 32 * wd;
+                    if (nb < 32) word &= (1u << nb) - 1u;
+                } else {
+                    const int b0 = 32 * wd, b1 = min(b0 + 32, p.frame_bits);
+                    for (int q = b0 / p.bps; q * p.bps < b1; ++q) {
+                        int idx = symidx[q];
+                        for (int i = 0; i < p.bps; ++i) {
+                            int pos = q * p.bps + i;
+                            if (pos >= b0 && pos < b1 && ((idx >> (p.bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                        }
+                    }
+                }
+                raw[wd] = word;
+            }
+            __syncthreads();
+            const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+            for (int wd = tid; wd < fw; wd += T4_THREADS) {
+                uint32_t cw = raw[wd], o = cw;
+                if (p.scramble) {
+                    uint32_t prev = wd ? raw[wd - 1] : p.prev0;
+                    o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+                }
+                const int n = min(32, p.frame_bits - 32 * wd);
+                if (n < 32) o &= (1u << n) - 1u;
+                if (txbits) errs += __popc(o ^ bits_get32(txbits, base + 32 * (int64_t)wd, min(total_bits, base + p.frame_bits)));
+                if (outbits) bits_put(outbits, base + 32 * (int64_t)wd, n, o);
+            }
+            __syncthreads();
+        }
+        errs = block_sum(errs, red_i);
+        nears = block_sum(nears, red_i);
+        if (tid == 0 && counts) {
+            if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+            atomicAdd(&counts[1], (unsigned long long)stream_bits);
+            if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+        }
+        __syncthreads();
+    }
+}
+
 extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_t L, int W, int Nfft, void* autocorr, int32_t* tg_pos, double* freq_off,
                                 int32_t* fail);
 
@@ -294,8 +578,43 @@ extern "C" int ofdm_rx_chain_t4(ofdm_ctx* ctx, const ofdm_link_params* lp, const
         }
         const int fw = (p.frame_bits + 31) / 32;
         size_t smem = sizeof(float2) * (2 * (size_t)p.Nfft + (size_t)p.S * p.Np + p.S + p.Nc + 2 * (size_t)pl->n_knots) + sizeof(double) * (size_t)p.S * p.Np + sizeof(uint32_t) * fw + (size_t)p.SpF * p.Nd + 32;
-        if (rc == OFDM_OK && smem > 200 * 1024) rc = ctx_fail(ctx, OFDM_ERR_UNSUPPORTED, "stream shape needs %zu bytes of shared memory", smem);
-        if (rc == OFDM_OK) {
+        // fast path: Nfft = 1024, warp-per-symbol register FFT (rx_t4_fast_kernel)
+        bool fast_done = false;
+        if (rc == OFDM_OK && p.Nfft == 1024 && !getenv("OFDM_B200_NO_FAST")) {
+            const size_t tiles = sizeof(float2) * (size_t)(T4_THREADS / 32) * 32 * T4F_EROW, taus = sizeof(double) * (size_t)p.S * p.Np;
+            const size_t fsmem = (std::max(tiles, taus) + 15) / 16 * 16 + sizeof(float2) * (1024 + (size_t)p.S * p.Np + p.S + p.Nc + 2 * (size_t)pl->n_knots) +
+                                 sizeof(uint32_t) * fw + (size_t)p.SpF * p.Nd + 32;
+            if (fsmem <= 111 * 1024) {
+                std::vector<float> twt(2 * 1024);
+                for (int k1 = 0; k1 < 32; ++k1)
+                    for (int n2 = 0; n2 < 32; ++n2) {
+                        const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((n2 * k1) & 1023) / 1024.0L;
+                        twt[2 * (32 * k1 + n2)] = (float)cosl(a); twt[2 * (32 * k1 + n2) + 1] = (float)sinl(a);
+                    }
+                T4FastExtra fx;
+                fx.tw_t = (const float2*)ctx_blob(ctx, twt.data(), sizeof(float) * twt.size());
+                fx.two_a = 2.f * (float)ct.re[12];
+                const bool q16 = lp->constellation == OFDM_16QAM, near = near_eps > 0.0, small = p.Nc <= 416;
+                typedef void (*kern_t)(T4Params, T4FastExtra, PlanDev<float>, DevConst<float>, const float2*, int64_t, int64_t, const int32_t*, const double*, float2*,
+                                       const uint32_t*, int64_t, uint32_t*, unsigned long long*, int32_t*, double*, double*, float2*, float);
+                kern_t kern = small ? (q16 ? (near ? rx_t4_fast_kernel<13, true, true> : rx_t4_fast_kernel<13, true, false>)
+                                           : (near ? rx_t4_fast_kernel<13, false, true> : rx_t4_fast_kernel<13, false, false>))
+                                    : (q16 ? (near ? rx_t4_fast_kernel<32, true, true> : rx_t4_fast_kernel<32, true, false>)
+                                           : (near ? rx_t4_fast_kernel<32, false, true> : rx_t4_fast_kernel<32, false, false>));
+                if (fx.tw_t) {
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
+                    kern<<<grid, T4_THREADS, fsmem, ctx->stream>>>(p, fx, plan_dev<float>(pl), make_devconst<float>(lp->constellation), (const float2*)rx, B, L, tg_dev, fo_dev,
+                                                                   (float2*)scr, tx_bits, B * stream_bits, out_bits, (unsigned long long*)counts, ifo_dev, tau_dev,
+                                                                   phase_dev, (float2*)H_dev, (float)near_eps);
+                    ctx->launches++;
+                    cudaError_t e = cudaGetLastError();
+                    if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "rx_t4_fast_kernel launch failed: %s", cudaGetErrorString(e));
+                    fast_done = true;
+                }
+            }
+        }
+        if (rc == OFDM_OK && !fast_done && smem > 200 * 1024) rc = ctx_fail(ctx, OFDM_ERR_UNSUPPORTED, "stream shape needs %zu bytes of shared memory", smem);
+        if (rc == OFDM_OK && !fast_done) {
             cudaFuncSetAttribute(rx_t4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             rx_t4_kernel<<<grid, T4_THREADS, smem, ctx->stream>>>(p, plan_dev<float>(pl), make_devconst<float>(lp->constellation), (const float2*)rx, B, L, tg_dev, fo_dev,
                                                                    (float2*)scr, tx_bits, B * stream_bits, out_bits, (unsigned long long*)counts, ifo_dev, tau_dev,

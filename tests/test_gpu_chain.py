@@ -246,7 +246,11 @@ def test_rx_chain_task4_fused_matches_oracle_and_composed(G):
         assert close(fo[b], refs[b]["FreqOffset"], 2e-5) and close(tau[b], refs[b]["tau"], 2e-5) and close(ph[b], refs[b]["phase_shift"], 2e-3)
         Href = refs[b]["H"][:400]
         if np.all(np.isfinite(Href)):
-            assert np.linalg.norm(H[b] - Href) / np.linalg.norm(Href) < 1e-3
+            # phase_shift is a mean of wrapped angles (`fine_sync.m:47-52`): one pilot angle within rounding of +-pi
+            # moves it by 2*pi/n_kept (1.8e-3 here), and H carries exp(j*phase_shift).  Compare H with that
+            # (separately bounded) phase difference taken out.
+            dphi = ph[b] - refs[b]["phase_shift"]
+            assert np.linalg.norm(H[b] * np.exp(-1j * dphi) - Href) / np.linalg.norm(Href) < 1e-3
         else:
             n_nan += 1
             assert np.all(np.isnan(H[b].real))
