@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T4_THREADS / 32;
     const int M = p.Np * p.S;
-    // layout: [phase-1 tiles | phase-2 taus] (aliased) , wtab, Yp, rot_s, G, yk, dk, raw, symidx
+    // layout: [phase-1 tiles | phase-2 taus | phase-3 decisions] (aliased), wtab, Yp, rot_s, G, yk, dk
     const size_t tiles_bytes = sizeof(float2) * (size_t)NW * 32 * T4F_EROW;
     const size_t taus_bytes = sizeof(double) * (size_t)M;
     float2* tiles = (float2*)smem_raw;
@@ -290,9 +290,7 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
     float2* G = rot_s + p.S;                         // per-carrier correction / equaliser, Nc
     float2* yk = G + p.Nc;
     float2* dk = yk + plan.n_knots;
-    uint32_t* raw = (uint32_t*)(dk + plan.n_knots);
     const int fw = (p.frame_bits + 31) >> 5;
-    uint8_t* symidx = (uint8_t*)(((uintptr_t)(raw + fw) + 7) & ~(uintptr_t)7);   // SpF * Nd decisions, 8-byte aligned for the word-wise packer (+ slack)
     float2* E = tiles + warp * 32 * T4F_EROW;        // this warp's transpose tile
     const int SL = N + p.Tg;
     float2* Ysc = scratch + (int64_t)blockIdx.x * p.S * p.Nc;   // this CTA's parking area (stays in L2)
@@ -366,7 +364,8 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         }
         __syncthreads();
         // ---- OFDM_demodulator, one warp per symbol; park the useful bins (rotated), keep the pilots
-        for (int s = warp; s < p.S; s += NW) {
+        // (warp 0 spent a transform on the IFO search: the deal starts at warp 1 so that it gets the short share)
+        for (int s = (warp + NW - 1) % NW; s < p.S; s += NW) {
             float2 v[32];
             load_window(r, (int64_t)s * SL + p.Tg, tg, tshift, v);
             if (p.freq_desync) {
@@ -392,8 +391,10 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         double tau = 0.0, phase = 0.0;
         if (p.time_desync || p.freq_desync) {
             const double deltak = (double)(p.pil0[1] - p.pil0[0]);
+            // The pilots are FP32 DFT outputs: the products are formed in double, the angle itself in FP32 (its
+            // argument carries no more than FP32 accuracy), sums and thresholds in double as in the reference.
             auto q_at = [&](int i) -> double2 { return cmulc(p.pilots_d[i], to_d(Yp[i])); };   // tx * conj(rx), flat column-major index
-            auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return atan2(d.y, d.x) / (2.0 * CUDART_PI * deltak); };
+            auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return (double)atan2f((float)d.y, (float)d.x) / (2.0 * CUDART_PI * deltak); };
             const int n = M - 1;
             for (int j = tid; j < n; j += T4_THREADS) taus[j] = tau_at(j);                  // taus(j+1) of the reference (:25-30)
             __syncthreads();
@@ -414,13 +415,22 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
             sum = block_sum(sum, red);
             double nk = block_sum((double)kept, red);
             tau = sum / nk;
+            // exp(+2j*pi*tau*k) at the pilot carriers, once per carrier (`fine_sync.m:38-44`); dk is free until the spline
+            double2* prot = (double2*)taus;                                                 // taus is dead from here on
+            __syncthreads();
+            for (int q = tid; q < p.Np; q += T4_THREADS) {
+                double sn = 0.0, cs = 1.0;
+                if (p.time_desync) sincospi(2.0 * tau * (double)p.pil0[q], &sn, &cs);
+                prot[q] = make_double2(cs, sn);
+            }
+            __syncthreads();
             double ps = 0; int pn = 0;
             for (int i = tid; i < M; i += T4_THREADS) {
                 const int pq = i % p.Np;
                 double2 rxv = to_d(Yp[i]);
-                if (p.time_desync) { double sn, cs; sincospi(2.0 * tau * (double)p.pil0[pq], &sn, &cs); rxv = cmul(rxv, make_double2(cs, sn)); }
+                if (p.time_desync) rxv = cmul(rxv, prot[pq]);
                 double2 qq = cmulc(p.pilots_d[i], rxv);
-                double a = atan2(qq.y, qq.x);
+                double a = (double)atan2f((float)qq.y, (float)qq.x);
                 if (fabs(a) > 1e-3) { ps += a; ++pn; }
             }
             ps = block_sum(ps, red);
@@ -457,59 +467,68 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
             });
             __syncthreads();
         }
-        // ---- get_payload, demapping, DeScrambler, BER: one frame (SpF symbols) per round
+        // ---- get_payload + demapping for the whole stream (decisions alias the tile/taus region, free by now)
         int errs = 0, nears = 0;
-        for (int f = 0; f < p.frames; ++f) {
-            for (int sf = 0; sf < p.SpF; ++sf) {
-                const float2* Ys = Ysc + (int64_t)(f * p.SpF + sf) * p.Nc;
-                uint8_t* sp = symidx + sf * p.Nd;
-                for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
-                    const int cidx = p.data0[dr];
-                    const float2 e = (cidx < p.Nc) ? cmul(Ys[cidx], G[cidx]) : make_float2(0.f, 0.f);
-                    float margin = 1.f;
-                    uint32_t code;
-                    if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
-                    else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
-                    if (NEAR && margin < near_eps) ++nears;
-                    sp[dr] = (uint8_t)code;
-                }
+        uint8_t* dec = (uint8_t*)smem_raw;             // [S][Nd] codes
+        __syncthreads();
+        for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
+            const int cidx = p.data0[dr];
+            const bool in = cidx < p.Nc;
+            const float2 g = in ? G[cidx] : make_float2(0.f, 0.f);
+            const float2* Yc = Ysc + (in ? cidx : 0);
+            for (int s0 = 0; s0 < p.S; s0 += 10) {
+                float2 y[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) y[u] = (s0 + u < p.S) ? Yc[(int64_t)(s0 + u) * p.Nc] : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 10; ++u)
+                    if (s0 + u < p.S) {
+                        const float2 e = in ? cmul(y[u], g) : make_float2(0.f, 0.f);
+                        float margin = 1.f;
+                        uint32_t code;
+                        if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
+                        else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                        if (NEAR && margin < near_eps) ++nears;
+                        dec[(s0 + u) * p.Nd + dr] = (uint8_t)code;
+                    }
             }
-            __syncthreads();
-            for (int wd = tid; wd < fw; wd += T4_THREADS) {
+        }
+        __syncthreads();
+        // ---- DeScrambler + BER, frame by frame without barriers: a thread packs word wd and its predecessor itself
+        {
+            const int fpb = p.SpF * p.Nd;              // decisions per frame
+            auto packed = [&](const uint8_t* fr, int wd) -> uint32_t {
                 uint32_t word = 0;
-                if (QAM16) {
-                    const uint2 by = *reinterpret_cast<const uint2*>(symidx + 8 * wd);   // 8 ready-made nibbles, one per byte
-                    uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
-                    uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
-                    word = lo | (hi << 16);
-                    const int nb = p.frame_bits - 32 * wd;
-                    if (nb < 32) word &= (1u << nb) - 1u;
+                if (QAM16) {                           // eight ready-made nibbles, one per byte (frames need not be 8-aligned in `dec`)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { const int q = 8 * wd + j; if (q < fpb) word |= (uint32_t)fr[q] << (4 * j); }
                 } else {
                     const int b0 = 32 * wd, b1 = min(b0 + 32, p.frame_bits);
                     for (int q = b0 / p.bps; q * p.bps < b1; ++q) {
-                        int idx = symidx[q];
+                        int idx = fr[q];
                         for (int i = 0; i < p.bps; ++i) {
                             int pos = q * p.bps + i;
                             if (pos >= b0 && pos < b1 && ((idx >> (p.bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
                         }
                     }
                 }
-                raw[wd] = word;
-            }
-            __syncthreads();
-            const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
-            for (int wd = tid; wd < fw; wd += T4_THREADS) {
-                uint32_t cw = raw[wd], o = cw;
+                return word;
+            };
+            for (int item = tid; item < p.frames * fw; item += T4_THREADS) {
+                const int f = item / fw, wd = item - f * fw;
+                const uint8_t* fr = dec + (size_t)f * fpb;
+                const uint32_t cw = packed(fr, wd);
+                uint32_t o = cw;
                 if (p.scramble) {
-                    uint32_t prev = wd ? raw[wd - 1] : p.prev0;
+                    const uint32_t prev = wd ? packed(fr, wd - 1) : p.prev0;
                     o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
                 }
                 const int n = min(32, p.frame_bits - 32 * wd);
                 if (n < 32) o &= (1u << n) - 1u;
+                const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
                 if (txbits) errs += __popc(o ^ bits_get32(txbits, base + 32 * (int64_t)wd, min(total_bits, base + p.frame_bits)));
                 if (outbits) bits_put(outbits, base + 32 * (int64_t)wd, n, o);
             }
-            __syncthreads();
         }
         errs = block_sum(errs, red_i);
         nears = block_sum(nears, red_i);
@@ -582,9 +601,8 @@ extern "C" int ofdm_rx_chain_t4(ofdm_ctx* ctx, const ofdm_link_params* lp, const
         bool fast_done = false;
         if (rc == OFDM_OK && p.Nfft == 1024 && !getenv("OFDM_B200_NO_FAST")) {
             const size_t tiles = sizeof(float2) * (size_t)(T4_THREADS / 32) * 32 * T4F_EROW, taus = sizeof(double) * (size_t)p.S * p.Np;
-            const size_t fsmem = (std::max(tiles, taus) + 15) / 16 * 16 + sizeof(float2) * (1024 + (size_t)p.S * p.Np + p.S + p.Nc + 2 * (size_t)pl->n_knots) +
-                                 sizeof(uint32_t) * fw + (size_t)p.SpF * p.Nd + 32;
-            if (fsmem <= 111 * 1024) {
+            const size_t fsmem = (std::max(tiles, taus) + 15) / 16 * 16 + sizeof(float2) * (1024 + (size_t)p.S * p.Np + p.S + p.Nc + 2 * (size_t)pl->n_knots) + 32;
+            if (fsmem <= 111 * 1024 && (size_t)p.S * p.Nd <= std::max(tiles, taus)) {
                 std::vector<float> twt(2 * 1024);
                 for (int k1 = 0; k1 < 32; ++k1)
                     for (int n2 = 0; n2 < 32; ++n2) {
