@@ -1,5 +1,6 @@
 // AutoCorrFunction / remove_IFO / fine_sync -- Task-4 synchronisation on B independent streams.
 #include "fft.cuh"
+#include <type_traits>
 
 // =====================================================================================
 // AutoCorrFunction (`Task 5/AutoCorrFunction.m:1-28`)
@@ -96,6 +97,81 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __res
     }
 }
 
+// FP32 specialisation of the pass above: one float4 {Re num, Im num, |x|^2, |y|^2} per sample in shared memory
+// (group stride 17 entries: 128-bit accesses of a quarter warp land in eight different bank groups), packed
+// FADD2 for the two pairs.  Same groups, same order of additions, hence the same bits as the generic kernel.
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) {
+    const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <bool ALIGNED>
+__global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out, int tile,
+                                                                  float2* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NE = AC_THREADS * AC_G;                 // samples staged per block
+    float4* Q = (float4*)smem_raw;                    // NE + NE/16 entries
+    const int64_t b = blockIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.y * tile;
+    const float2* r = rx + b * L;
+    const int tid = threadIdx.x;
+#pragma unroll 4
+    for (int i = tid; i < NE; i += AC_THREADS) {
+        const int64_t n = n0 + i;
+        float2 x = make_float2(0.f, 0.f), y = make_float2(0.f, 0.f);
+        if (n + Nfft < L) { x = r[n]; y = r[n + Nfft]; }
+        Q[i + (i >> 4)] = make_float4(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y, x.x * x.x + x.y * x.y, y.x * y.x + y.y * y.y);   // x * conj(y), |x|^2, |y|^2
+    }
+    __syncthreads();
+    float4 sfx[AC_G];                                 // suffix sums of the own group
+    {
+        const int q0 = tid * (AC_G + 1);
+        float4 v[AC_G];
+#pragma unroll
+        for (int i = 0; i < AC_G; ++i) v[i] = Q[q0 + i];
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = AC_G - 1; i >= 0; --i) { a = f4add(a, v[i]); sfx[i] = a; }
+        a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < AC_G; ++i) { a = f4add(a, v[i]); Q[q0 + i] = a; }    // prefix sums back to shared memory
+    }
+    __syncthreads();
+    const int wq = W >> 4, wr = W & 15;
+    uint32_t mask16 = 0;
+    if (tid * AC_G < tile) {
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = tid + 1; j < tid + wq; ++j) m = f4add(m, Q[j * (AC_G + 1) + AC_G - 1]);
+        const int qg = (tid + wq) * (AC_G + 1);
+        const float4 g = Q[qg + AC_G - 1];
+        const int64_t nb = n0 + tid * AC_G;
+        const bool full = (nb + AC_G <= n_out) && (nb + 1 > (int64_t)W);
+#pragma unroll
+        for (int rr = 0; rr < AC_G; ++rr) {
+            float4 t = f4add(sfx[rr], m);
+            if (ALIGNED) {
+                if (rr > 0) t = f4add(t, Q[qg + rr - 1]);
+            } else {
+                int oe = rr + wr;
+                int qt = qg;
+                if (oe >= AC_G) { t = f4add(t, g); oe -= AC_G; qt += AC_G + 1; }
+                if (oe > 0) t = f4add(t, Q[qt + oe - 1]);
+            }
+            const int64_t n = nb + rr;
+            const bool above = (t.x * t.x + t.y * t.y) > (float)(0.77 * 0.77) * (t.z * t.w);
+            if (above && (full || (n < n_out && n + 1 > (int64_t)W))) mask16 |= 1u << rr;
+            if (ac_out && n < n_out) {
+                const float den = sqrtf(t.z * t.w);
+                ac_out[b * n_out + n] = make_float2(t.x / den, t.y / den);   // 0/0 -> NaN as in MATLAB
+            }
+        }
+    }
+    const uint32_t hi = __shfl_down_sync(0xffffffffu, mask16, 1);
+    if ((tid & 1) == 0 && tid * AC_G < tile) {
+        const int64_t wi = (n0 + tid * AC_G) >> 5;
+        if (wi < flag_words) flags[b * flag_words + wi] = mask16 | (hi << 16);
+    }
+}
+
 template <typename T>
 __global__ void autocorr_detect_kernel(const cx<T>* __restrict__ rx, int64_t B, int64_t L, int W, int Nfft, int64_t n_out,
                                        const uint32_t* __restrict__ flags, int64_t flag_words, int32_t* __restrict__ tg_pos,
@@ -166,9 +242,14 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
     const int tiles = (int)cdiv64(n_out, tile);
     DISPATCH_T(ctx, {
         size_t smem = 4 * sizeof(T) * (size_t)(AC_THREADS * AC_G + AC_THREADS);
-        auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
-        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_out, tile, (cx<T>*)autocorr, flags, flag_words);
+        if constexpr (std::is_same<T, float>::value) {
+            auto k1 = (W & 15) ? autocorr_f32_kernel<false> : autocorr_f32_kernel<true>;
+            k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const float2*)rx, L, W, Nfft, n_out, tile, (float2*)autocorr, flags, flag_words);
+        } else {
+            auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_out, tile, (cx<T>*)autocorr, flags, flag_words);
+        }
         ctx->launches++;
         autocorr_detect_kernel<T><<<(unsigned)cdiv64(B * 32, 128), 128, 0, ctx->stream>>>((const cx<T>*)rx, B, L, W, Nfft, n_out, flags, flag_words,
                                                                                             tg_pos, freq_off, fail);
