@@ -140,6 +140,20 @@ OFDM_API int ofdm_mp_channel_resp(ofdm_ctx*, const double* taps_host, int K, int
 OFDM_API int ofdm_apply_fir(ofdm_ctx*, const void* in_dev, int64_t B, int64_t L, const void* h_dev, int D,
                             int h_per_stream, void* out_dev);
 
+/* Static tapped-delay-line fading channel standing in for `lteFadingChannel` as used by `Task 5/Task5_part2.m:27-34,
+ * 152-154` (DopplerFreq 0, one realisation per Monte-Carlo run): profile 0 EPA, 1 EVA, 2 ETU (3GPP TS 36.101 B.2.1),
+ * Rayleigh tap gains from Philox keyed by (seed, first_stream_id + b), fractional delays by a windowed-sinc
+ * interpolator with a lead of 7 samples.  LTE Toolbox internals are not public: draws differ from MATLAB's.
+ * ofdm_tdl_info: n_paths (= dominant_taps of the MP/OMP calls), h_len, path delays in samples (<= 9 doubles).
+ * ofdm_tdl_channel: h_dev B x h_len complex impulse responses (feed to ofdm_apply_fir, h_per_stream = 1),
+ * gains_dev optional B x n_paths. */
+OFDM_API int ofdm_tdl_info(int profile, double fs_hz, int* n_paths, int* h_len, double* delays_samples);
+OFDM_API int ofdm_tdl_channel(ofdm_ctx*, int profile, double fs_hz, int64_t B, uint64_t seed, int64_t first_stream_id,
+                              int h_len, void* h_dev, void* gains_dev);
+/* (H - Hest)(H - Hest)' / n per stream (`Task 5/Task5_part2.m:200-203`): out_dev B doubles. */
+OFDM_API int ofdm_mse(ofdm_ctx*, const void* a_dev, int64_t a_stride, const void* b_dev, int64_t b_stride, int64_t B,
+                      int n, double* out_dev);
+
 /* ---- a14-a16  AutoCorrFunction / remove_IFO / fine_sync ----------------------------------- */
 /* (`Task 5/AutoCorrFunction.m:1-28`) autocorr_dev optional: B x (L-W-Nfft) complex.
  * tg_pos_dev: B int32 (1-based, 65 on detector failure), freq_off_dev: B doubles,
@@ -176,6 +190,11 @@ OFDM_API int ofdm_interpolate(ofdm_ctx*, const void* Hp_dev, int64_t B, const in
 /* (`Task 5/equalize_signal.m:1-8`) H_dev: B x h_stride (>= N_carrier); rows > N_carrier become 0. */
 OFDM_API int ofdm_equalize(ofdm_ctx*, const void* grid_dev, int64_t B, int S, int Nfft, const void* H_dev,
                            int h_stride, int N_carrier, void* out_dev);
+
+/* Measurement vector of the sparse estimators, `Y = RX(pilotCarriers,1)./pilotValues(:,1)`
+ * (`Task 5/Main_model_Task_5.m:191`, `Task5_part2.m:190`): y_dev B x Np from grid_dev B x S x Nfft. */
+OFDM_API int ofdm_pilot_ls(ofdm_ctx*, const void* grid_dev, int64_t B, int S, int Nfft, const int32_t* pilot_loc_host,
+                           int Np, const double* Xp_host, void* y_dev);
 
 /* ---- a22/a23  OMP_estimate / MP_estimate  (`Task 5/OMP_estimate.m:2-37`, `MP_estimate.m:2-34`) */
 /* y_dev: B x Np.  Dictionary: either dense `A_dev` (Np x Ldict, column-major as MATLAB stores

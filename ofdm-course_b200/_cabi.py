@@ -56,6 +56,9 @@ SIGNATURES = {
     "ofdm_add_noise": (i32, [vp, vp, i64, i64, vp, vp, u64, i64, vp, vp]),
     "ofdm_mp_channel_resp": (i32, [vp, pdbl, i32, i32, pdbl, i32, C.POINTER(i32), vp]),
     "ofdm_apply_fir": (i32, [vp, vp, i64, i64, vp, i32, i32, vp]),
+    "ofdm_tdl_info": (i32, [i32, dbl, C.POINTER(i32), C.POINTER(i32), pdbl]),
+    "ofdm_tdl_channel": (i32, [vp, i32, dbl, i64, u64, i64, i32, vp, vp]),
+    "ofdm_mse": (i32, [vp, vp, i64, vp, i64, i64, i32, vp]),
     "ofdm_cp_autocorr": (i32, [vp, vp, i64, i64, i32, i32, vp, vp, vp, vp]),
     "ofdm_remove_ifo": (i32, [vp, vp, i64, i64, i32, vp, vp]),
     "ofdm_fine_sync": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, i32, i32, vp, vp, vp]),
@@ -64,6 +67,7 @@ SIGNATURES = {
     "ofdm_mmse_ce": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, i32, vp, i32, vp, vp]),
     "ofdm_interpolate": (i32, [vp, vp, i64, pi32, i32, i32, i32, vp]),
     "ofdm_equalize": (i32, [vp, vp, i64, i32, i32, vp, i32, i32, vp]),
+    "ofdm_pilot_ls": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, vp]),
     "ofdm_omp": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp, vp]),
     "ofdm_mp": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp]),
     "ofdm_ber_count": (i32, [vp, vp, vp, i64, vp]),

@@ -178,3 +178,96 @@ extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t
     CUDA_TRY(ctx, cudaMemcpyAsync(rx, tx, esz * B * L, cudaMemcpyDeviceToDevice, ctx->stream));
     return OFDM_OK;
 }
+
+// ---- static tapped-delay-line fading channel (stands in for `lteFadingChannel`, `Task 5/Task5_part2.m:27-34,152-154`)
+// The reference draws one static realisation per Monte-Carlo run (DopplerFreq = 0, InitPhase "Random", per-run Seed)
+// of the LTE EPA / EVA / ETU profile at SamplingRate 4e7 and obtains its impulse response by filtering a unit
+// impulse.  LTE Toolbox source is not available, so this is the PUBLISHED model only -- 3GPP TS 36.101 Annex B.2.1
+// tap delays and relative powers, Rayleigh tap gains normalised to unit total average power, fractional delays by
+// a Hann-windowed sinc interpolator with a fixed lead of TDL_LEAD samples -- and its draws do not reproduce
+// MATLAB's (parity unpinned; imported taps go through ofdm_apply_fir directly).
+#define TDL_LEAD 7
+#define TDL_MAXP 9
+struct TdlProfile { int n; double delay_ns[TDL_MAXP]; double power_db[TDL_MAXP]; };
+static const TdlProfile TDL_TABLE[3] = {
+    {7, {0, 30, 70, 90, 110, 190, 410, 0, 0}, {0.0, -1.0, -2.0, -3.0, -8.0, -17.2, -20.8, 0, 0}},                       // EPA
+    {9, {0, 30, 150, 310, 370, 710, 1090, 1730, 2510}, {0.0, -1.5, -1.4, -3.6, -0.6, -9.1, -7.0, -12.0, -16.9}},       // EVA
+    {9, {0, 50, 120, 200, 230, 500, 1600, 2300, 5000}, {-1.0, -1.0, -1.0, 0.0, 0.0, 0.0, -3.0, -5.0, -7.0}}};          // ETU
+struct TdlDev { int n; float delay[TDL_MAXP]; float amp[TDL_MAXP]; };
+
+extern "C" int ofdm_tdl_info(int profile, double fs_hz, int* n_paths, int* h_len, double* delays_samples) {
+    if (profile < 0 || profile > 2 || !(fs_hz > 0)) return OFDM_ERR_INVALID;
+    const TdlProfile& t = TDL_TABLE[profile];
+    double dmax = 0;
+    for (int i = 0; i < t.n; ++i) { double d = t.delay_ns[i] * 1e-9 * fs_hz; if (delays_samples) delays_samples[i] = d; dmax = std::max(dmax, d); }
+    if (n_paths) *n_paths = t.n;
+    if (h_len) *h_len = (int)ceil(dmax) + 2 * TDL_LEAD + 1;
+    return OFDM_OK;
+}
+
+// one thread per (stream, tap of the impulse response): h[n] = sum_p g_p * w(n - LEAD - d_p), w = Hann-windowed sinc of half width LEAD
+template <typename T>
+__global__ void tdl_kernel(TdlDev t, int64_t B, int Lh, uint64_t seed, int64_t first_stream, cx<T>* __restrict__ h, cx<T>* __restrict__ gains) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Lh) return;
+    const int64_t b = i / Lh;
+    const int n = (int)(i - b * Lh);
+    float ar = 0.f, ai = 0.f;
+    for (int p = 0; p < t.n; ++p) {
+        float g1, g2;
+        philox_normal_pair(seed ^ 0x74646c5f63686e6cULL, (uint64_t)(first_stream + b), (uint64_t)p, g1, g2);   // own key space ("tdl_chnl")
+        const float gr = t.amp[p] * g1 * 0.70710678118654752f, gi = t.amp[p] * g2 * 0.70710678118654752f;
+        if (n == 0 && gains) gains[b * t.n + p] = mk<T>((T)gr, (T)gi);
+        const float x = (float)n - (float)TDL_LEAD - t.delay[p];
+        float w = 0.f;
+        if (fabsf(x) < (float)TDL_LEAD) {
+            const float sinc = (x == 0.f) ? 1.f : sinpif(x) / (3.14159265358979323846f * x);
+            w = sinc * (0.5f + 0.5f * cospif(x / (float)TDL_LEAD));
+        }
+        ar += gr * w; ai += gi * w;
+    }
+    h[i] = mk<T>((T)ar, (T)ai);
+}
+extern "C" int ofdm_tdl_channel(ofdm_ctx* ctx, int profile, double fs_hz, int64_t B, uint64_t seed, int64_t first_stream_id, int h_len,
+                                void* h_dev, void* gains_dev) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    int np = 0, need = 0;
+    REQUIRE(ctx, ofdm_tdl_info(profile, fs_hz, &np, &need, nullptr) == OFDM_OK, "unknown delay profile or sampling rate");
+    REQUIRE(ctx, h_dev && B >= 0 && h_len >= need, "h_dev missing or shorter than ofdm_tdl_info's h_len");
+    if (B == 0) return OFDM_OK;
+    const TdlProfile& t = TDL_TABLE[profile];
+    TdlDev d;
+    d.n = t.n;
+    double ptot = 0;
+    for (int i = 0; i < t.n; ++i) ptot += pow(10.0, t.power_db[i] / 10.0);
+    for (int i = 0; i < TDL_MAXP; ++i) {
+        d.delay[i] = i < t.n ? (float)(t.delay_ns[i] * 1e-9 * fs_hz) : 0.f;
+        d.amp[i] = i < t.n ? (float)sqrt(pow(10.0, t.power_db[i] / 10.0) / ptot) : 0.f;
+    }
+    DISPATCH_T(ctx, { tdl_kernel<T><<<(unsigned)cdiv64(B * h_len, 128), 128, 0, ctx->stream>>>(d, B, h_len, seed, first_stream_id, (cx<T>*)h_dev, (cx<T>*)gains_dev); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
+// ---- channel-estimate error of `Task5_part2.m:200-203`: (H - Hest)(H - Hest)' / N per stream, accumulated in double
+template <typename T>
+__global__ void mse_kernel(const cx<T>* __restrict__ a, int64_t a_stride, const cx<T>* __restrict__ bb, int64_t b_stride, int n, double* __restrict__ out) {
+    __shared__ double red[32];
+    const int64_t s = blockIdx.x;
+    double acc = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const cx<T> x = a[s * a_stride + k], y = bb[s * b_stride + k];
+        const double dr = (double)x.x - (double)y.x, di = (double)x.y - (double)y.y;
+        acc += dr * dr + di * di;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[s] = acc / (double)n;
+}
+extern "C" int ofdm_mse(ofdm_ctx* ctx, const void* a_dev, int64_t a_stride, const void* b_dev, int64_t b_stride, int64_t B, int n, double* out_dev) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, a_dev && b_dev && out_dev && B >= 0 && n > 0 && a_stride >= n && b_stride >= n, "bad argument");
+    if (B == 0) return OFDM_OK;
+    DISPATCH_T(ctx, { mse_kernel<T><<<(unsigned)B, 256, 0, ctx->stream>>>((const cx<T>*)a_dev, a_stride, (const cx<T>*)b_dev, b_stride, n, out_dev); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}

@@ -202,6 +202,29 @@ extern "C" int ofdm_ls_ce(ofdm_ctx* ctx, const void* grid, int64_t B, int S, int
     return OFDM_OK;
 }
 
+// ---- Y = RX(pilotCarriers, 1) ./ pilotValues(:, 1): the measurement vector handed to MP/OMP
+// (`Task 5/Main_model_Task_5.m:191`, `Task5_part2.m:190`)
+template <typename T>
+__global__ void pilot_ls_kernel(const cx<T>* __restrict__ grid, int64_t stream_stride, int64_t B, const int32_t* __restrict__ loc0, int Np,
+                                const cx<T>* __restrict__ xp, cx<T>* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Np) return;
+    const int64_t b = i / Np;
+    const int q = (int)(i - b * Np);
+    y[i] = cdiv(grid[b * stream_stride + loc0[q]], xp[q]);
+}
+extern "C" int ofdm_pilot_ls(ofdm_ctx* ctx, const void* grid, int64_t B, int S, int Nfft, const int32_t* loc, int Np, const double* pv, void* y) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, grid && y && loc && pv && Np >= 1 && S > 0 && B >= 0, "bad argument");
+    const int32_t* l0; int rc = pilots0(ctx, loc, Np, Nfft, &l0); if (rc) return rc;
+    if (B == 0) return OFDM_OK;
+    const void* xp = ofdm_upload_pilots(ctx, pv, Np);
+    REQUIRE(ctx, xp != nullptr, "pilot upload failed");
+    DISPATCH_T(ctx, { pilot_ls_kernel<T><<<(unsigned)cdiv64(B * Np, 256), 256, 0, ctx->stream>>>((const cx<T>*)grid, (int64_t)S * Nfft, B, l0, Np, (const cx<T>*)xp, (cx<T>*)y); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
 extern "C" int ofdm_estimate_channel(ofdm_ctx* ctx, const void* grid, int64_t B, int S, int Nfft, const int32_t* allc, int Nq, const int32_t* pc, int Np,
                                      const double* pv, void* H, void* Hp) {
     if (!ctx) return OFDM_ERR_INVALID;

@@ -114,12 +114,27 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* 
     const int64_t n0 = (int64_t)blockIdx.y * tile;
     const float2* r = rx + b * L;
     const int tid = threadIdx.x;
-#pragma unroll 4
-    for (int i = tid; i < NE; i += AC_THREADS) {
-        const int64_t n = n0 + i;
-        float2 x = make_float2(0.f, 0.f), y = make_float2(0.f, 0.f);
-        if (n + Nfft < L) { x = r[n]; y = r[n + Nfft]; }
-        Q[i + (i >> 4)] = make_float4(x.x * y.x + x.y * y.y, x.y * y.x - x.x * y.y, x.x * x.x + x.y * x.y, y.x * y.x + y.y * y.y);   // x * conj(y), |x|^2, |y|^2
+    // staging: sample n0 + 128 j + tid and its partner one FFT length later, all loads of a thread in flight at once
+    {
+        float2 x[AC_G], y[AC_G];
+        const float2* rp = r + n0 + tid;
+        if (n0 + NE + Nfft <= L) {                    // interior tile: no bounds checks
+#pragma unroll
+            for (int j = 0; j < AC_G; ++j) { x[j] = __ldg(rp + AC_THREADS * j); y[j] = __ldg(rp + AC_THREADS * j + Nfft); }
+        } else {
+#pragma unroll
+            for (int j = 0; j < AC_G; ++j) {
+                const bool ok = n0 + tid + AC_THREADS * j + Nfft < L;
+                x[j] = ok ? __ldg(rp + AC_THREADS * j) : make_float2(0.f, 0.f);
+                y[j] = ok ? __ldg(rp + AC_THREADS * j + Nfft) : make_float2(0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < AC_G; ++j) {
+            const int i = tid + AC_THREADS * j;
+            Q[i + (i >> 4)] = make_float4(x[j].x * y[j].x + x[j].y * y[j].y, x[j].y * y[j].x - x[j].x * y[j].y, x[j].x * x[j].x + x[j].y * x[j].y,
+                                          y[j].x * y[j].x + y[j].y * y[j].y);   // x * conj(y), |x|^2, |y|^2
+        }
     }
     __syncthreads();
     float4 sfx[AC_G];                                 // suffix sums of the own group
@@ -156,13 +171,21 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* 
                 if (oe >= AC_G) { t = f4add(t, g); oe -= AC_G; qt += AC_G + 1; }
                 if (oe > 0) t = f4add(t, Q[qt + oe - 1]);
             }
-            const int64_t n = nb + rr;
             const bool above = (t.x * t.x + t.y * t.y) > (float)(0.77 * 0.77) * (t.z * t.w);
-            if (above && (full || (n < n_out && n + 1 > (int64_t)W))) mask16 |= 1u << rr;
-            if (ac_out && n < n_out) {
-                const float den = sqrtf(t.z * t.w);
-                ac_out[b * n_out + n] = make_float2(t.x / den, t.y / den);   // 0/0 -> NaN as in MATLAB
+            if (above) mask16 |= 1u << rr;
+            if (ac_out) {
+                const int64_t n = nb + rr;
+                if (n < n_out) {
+                    const float den = sqrtf(t.z * t.w);
+                    ac_out[b * n_out + n] = make_float2(t.x / den, t.y / den);   // 0/0 -> NaN as in MATLAB
+                }
             }
+        }
+        if (!full) {                                   // edge groups: drop positions outside (W, n_out]
+            uint32_t keep = 0;
+#pragma unroll
+            for (int rr = 0; rr < AC_G; ++rr) { const int64_t n = nb + rr; if (n < n_out && n + 1 > (int64_t)W) keep |= 1u << rr; }
+            mask16 &= keep;
         }
     }
     const uint32_t hi = __shfl_down_sync(0xffffffffu, mask16, 1);

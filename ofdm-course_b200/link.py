@@ -22,6 +22,7 @@ import torch
 from . import _cabi
 
 CONSTELLATIONS = {"BPSK": 1, "QPSK": 2, "8PSK": 3, "16QAM": 4}
+TDL_PROFILES = {"EPA": 0, "EVA": 1, "ETU": 2}
 DEFAULT_REGISTER = np.array([1, 0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0], dtype=np.uint8)
 
 
@@ -270,6 +271,30 @@ class Context:
         self._chk(self.lib.ofdm_apply_fir(self.h, self.p(x_dev), B, L, self.p(h_dev), D, 1 if per_stream else 0, self.p(out)))
         return out
 
+    def tdl_info(self, profile, fs_hz):
+        """(n_paths, h_len, delays in samples) of the EPA / EVA / ETU tapped-delay-line model at `fs_hz`."""
+        n, hl = C.c_int(0), C.c_int(0)
+        d = np.zeros(9, dtype=np.float64)
+        rc = self.lib.ofdm_tdl_info(TDL_PROFILES[str(profile).upper()], float(fs_hz), C.byref(n), C.byref(hl), d.ctypes.data_as(_cabi.pdbl))
+        if rc != 0:
+            raise OfdmError(f"status {rc}: unknown delay profile {profile!r} or sampling rate")
+        return n.value, hl.value, d[: n.value]
+
+    def tdl_channel(self, profile, fs_hz, B, seed=0, first_stream_id=0, want_gains=False):
+        """Static fading realisations standing in for lteFadingChannel (`Task5_part2.m:152-154`): h (B x h_len)."""
+        n, hl, _ = self.tdl_info(profile, fs_hz)
+        h = self.empty_c(B, hl)
+        g = self.empty_c(B, n) if want_gains else None
+        self._chk(self.lib.ofdm_tdl_channel(self.h, TDL_PROFILES[str(profile).upper()], float(fs_hz), B, seed, first_stream_id, hl, self.p(h), self.p(g)))
+        return (h, g) if want_gains else h
+
+    def mse(self, a_dev, b_dev, n):
+        """Per-stream mean |a - b|^2 over the first n entries of each row (`Task5_part2.m:200-203`)."""
+        B = a_dev.shape[0]
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        self._chk(self.lib.ofdm_mse(self.h, self.p(a_dev), a_dev.shape[-1], self.p(b_dev), b_dev.shape[-1], B, n, self.p(out)))
+        return out
+
     # ---------------------------------------------------------------- a14-a16
     def cp_autocorr(self, rx_dev, W, Nfft, want_autocorr=False):
         B, L = rx_dev.shape
@@ -339,6 +364,15 @@ class Context:
         out = torch.empty_like(grid_dev)
         self._chk(self.lib.ofdm_equalize(self.h, self.p(grid_dev), B, S, Nfft, self.p(H_dev), H_dev.shape[-1], N_carrier, self.p(out)))
         return out
+
+    def pilot_ls(self, grid_dev, Xp, pilot_loc):
+        """`Y = RX(pilotCarriers,1)./pilotValues(:,1)` (`Main_model_Task_5.m:191`): B x Np."""
+        B, S, Nfft = grid_dev.shape
+        pc, pp = _i32(pilot_loc)
+        pv, pvp = _f64c(np.asarray(Xp, dtype=np.complex128).reshape(pc.size, -1)[:, 0])
+        y = self.empty_c(B, pc.size)
+        self._chk(self.lib.ofdm_pilot_ls(self.h, self.p(grid_dev), B, S, Nfft, pp, pc.size, pvp, self.p(y)))
+        return y
 
     # ---------------------------------------------------------------- a22/a23
     def _pursuit(self, omp, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None):

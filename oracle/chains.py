@@ -202,3 +202,87 @@ def read_payload_bits(tiff_path, size_buffer):
     level = (np.mean(np.nonzero(sigma_b2 == mx)[0]) ) / 255.0     # graythresh: mean of maxima, (idx-1)/(nbins-1)
     bw = (img / 255.0) > level
     return bw.ravel(order="F")[:size_buffer].astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Task 5 part 2: comb sweep x Monte-Carlo runs x four estimators (`Task 5/Task5_part2.m`)
+
+def part2_combs(N_carrier=1024, lo=4, hi=256):
+    """`combs = 4:1:256` de-duplicated by floor(N_carrier/comb), first comb of each pilot count kept
+    (`Task5_part2.m:13-17`: unique() returns first occurrences, ascending in the value)."""
+    combs = np.arange(lo, hi + 1)
+    amounts = N_carrier // combs
+    _, ia = np.unique(amounts, return_index=True)
+    combs = combs[np.sort(ia)]
+    return combs, N_carrier // combs
+
+
+def params_part2(comb=None, pilotCarriers=None):
+    """Pilot layout and values of one sweep point (`Task5_part2.m:46-91`): regular comb `1:comb:N_carrier` or
+    a given sorted random mask (`sort(randperm(1024, Np))`, `:57-65`); alternating +-2*max|dict| pilots."""
+    p = LinkParams()
+    if pilotCarriers is None:
+        p.pilotCarriers, p.dataCarriers = F.pilot_layout_comb(p.N_carrier, comb)
+    else:
+        p.pilotCarriers = np.asarray(pilotCarriers, dtype=np.int64)
+        allc = np.arange(1, p.N_carrier + 1)
+        p.dataCarriers = allc[~np.isin(allc, p.pilotCarriers)]
+    p.pilotValues, _ = make_pilot_values(len(p.pilotCarriers), p.N_symb, p.Constellation, 2.0, True)
+    return p
+
+
+# 3GPP TS 36.101 Annex B.2.1 (the delay profiles `lteFadingChannel` implements; `Task5_part2.m:29`): ns, dB
+TDL_PROFILES = {
+    "EPA": ([0, 30, 70, 90, 110, 190, 410], [0.0, -1.0, -2.0, -3.0, -8.0, -17.2, -20.8]),
+    "EVA": ([0, 30, 150, 310, 370, 710, 1090, 1730, 2510], [0.0, -1.5, -1.4, -3.6, -0.6, -9.1, -7.0, -12.0, -16.9]),
+    "ETU": ([0, 50, 120, 200, 230, 500, 1600, 2300, 5000], [-1.0, -1.0, -1.0, 0.0, 0.0, 0.0, -3.0, -5.0, -7.0]),
+}
+TDL_LEAD = 7
+
+
+def tdl_amplitudes(profile):
+    """Tap amplitudes normalised to unit total average power (lteFadingChannel's NormalizePathGains default)."""
+    pw = 10.0 ** (np.asarray(TDL_PROFILES[profile][1]) / 10.0)
+    return np.sqrt(pw / pw.sum())
+
+
+def tdl_impulse_response(profile, fs_hz, path_gains):
+    """Impulse response of the static tapped-delay-line model for given complex path gains (the analogue of
+    `info.PathGains`, amplitudes included): Hann-windowed sinc interpolation of the fractional delays with a
+    lead of TDL_LEAD samples.  lteFadingChannel's own interpolator is not public -- this is the published
+    model only (PARITY UNPINNED against MATLAB)."""
+    d = np.asarray(TDL_PROFILES[profile][0], dtype=np.float64) * 1e-9 * fs_hz
+    n = np.arange(int(np.ceil(d.max())) + 2 * TDL_LEAD + 1, dtype=np.float64)
+    x = n[None, :] - TDL_LEAD - d[:, None]
+    w = np.where(np.abs(x) < TDL_LEAD, np.sinc(x) * (0.5 + 0.5 * np.cos(np.pi * x / TDL_LEAD)), 0.0)
+    return (np.asarray(path_gains)[:, None] * w).sum(axis=0)
+
+
+def part2_run(p: LinkParams, tx_noised, h_t, input_bits, n_paths, SNR_dB, Ldict):
+    """One Monte-Carlo run (`Task5_part2.m:148-304`) for a given static impulse response `h_t` (what
+    `lteFadingChannel(local_channel,[1; zeros(Nfft-1,1)])` returns, `:154`).  Returns NMSE[4], errors[4]
+    in the script's order LS, MMSE, MP, OMP."""
+    Nc = p.N_carrier
+    h_full = np.zeros(p.Nfft, dtype=np.complex128)
+    h_full[: len(h_t)] = h_t
+    rx = F.apply_channel(np.asarray(tx_noised), np.asarray(h_t))                           # :152 (filtering, first L samples)
+    H_f = np.fft.fft(h_full)                                                               # :155
+    X = rx.reshape((p.Nfft + p.T_Guard, p.N_symb), order="F")                              # :169
+    Y = F.OFDM_demodulator(X, p.T_Guard)                                                   # :172
+    H_ls = F.LS_CE(Y, p.pilotValues, p.pilotCarriers, Nc)                                  # :174
+    H_mmse = F.MMSE_CE(Y, p.pilotValues, p.pilotCarriers, p.Nfft, Nc, h_full[:Nc], SNR_dB)  # :176-177
+    A = F.sensing_matrix_dft(p.pilotCarriers, p.Nfft, Ldict)                               # :181-189
+    Yp = Y[p.pilotCarriers - 1, 0] / p.pilotValues[:, 0]                                   # :190
+    H_mp, _ = F.MP_estimate(Yp, A, p.Nfft, n_paths)                                        # :192
+    H_omp, _, _ = F.OMP_estimate(Yp, A, p.Nfft, n_paths, SNR_dB)                           # :193
+    ests = [H_ls, H_mmse, np.asarray(H_mp).ravel(), np.asarray(H_omp).ravel()]
+    nmse, errs = [], []
+    tx_bits = np.asarray(input_bits).ravel()
+    for H in ests:
+        e = H_f[:Nc] - np.asarray(H).ravel()[:Nc]
+        nmse.append(float(np.real(np.vdot(e, e))) / Nc)                                    # :200-203
+        eq = F.equalize_signal(Y, np.asarray(H).ravel(), Nc)                               # :269-272
+        rx_iq = F.get_payload(eq, p.dataCarriers).ravel(order="F")                         # :279-280
+        out_bits = F.demapping(-1, rx_iq, p.Constellation)                                 # :283
+        errs.append(int(np.sum(tx_bits != out_bits)))                                      # :303
+    return np.asarray(nmse), np.asarray(errs), {"H_f": H_f, "H": ests, "Y": Y}
