@@ -216,6 +216,15 @@ OFDM_API int ofdm_ber_count(ofdm_ctx*, const uint32_t* tx_bits_dev, const uint32
 /* sums_dev: 2 doubles {sum |ideal|^2, sum |ideal-rx|^2}, accumulated (+=). */
 OFDM_API int ofdm_mer(ofdm_ctx*, const void* iq_dev, int64_t n_sym, int constellation, double* sums_dev);
 
+/* ---- PAPR / CCDF  (`Task 5/calculatePAPR.m:2-11`, `calculate_window_PAPR.m:2-15`, `calculateCCDF.m:2-6`) ---- */
+/* x_dev: B x L streams.  papr_db_dev: B doubles = 10*log10(max|x|^2 / mean|x|^2). */
+OFDM_API int ofdm_papr(ofdm_ctx*, const void* x_dev, int64_t B, int64_t L, double* papr_db_dev);
+/* paprs_dev: B x (L - Nfft + 1) reals of the context's type: PAPR of every Nfft-sample window, O(L) per stream. */
+OFDM_API int ofdm_window_papr(ofdm_ctx*, const void* x_dev, int64_t B, int64_t L, int Nfft, void* paprs_dev);
+/* values_dev: n reals.  x_dev / ccdf_dev: capacity n + 1 reals; *n_out_dev entries are written:
+ * MATLAB's ecdf support points (the minimum twice) and 1 - F at them. */
+OFDM_API int ofdm_ccdf(ofdm_ctx*, const void* values_dev, int64_t n, void* x_dev, void* ccdf_dev, int64_t* n_out_dev);
+
 /* ---- fused chains (the hot path) ----------------------------------------------------------- */
 typedef struct ofdm_link_params {
     int32_t Nfft, Tg, N_carrier, S, SpF; /* S symbols per stream, SpF symbols per scrambler frame */

@@ -438,6 +438,51 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         chk(ofdm_mer(g_ctx, to_dev_complex(A(0), n), (int64_t)n, constellation_id(A(1)), s), op);
         chk(ofdm_d2h(g_ctx, sh, s, 16), "d2h");
         OUT(0, mxCreateDoubleScalar(10.0 * log10(sh[0] / sh[1])));
+    } else if (!strcmp(op, "calculatePAPR")) {                               /* PAPR = f(OFDM_signal) */
+        NEED(1);
+        size_t n = mxGetNumberOfElements(A(0));
+        double* d = (double*)devbuf(8);
+        chk(ofdm_papr(g_ctx, to_dev_complex(A(0), n), 1, (int64_t)n, d), op);
+        OUT(0, scalar_from_dev_f64(d));
+    } else if (!strcmp(op, "calculate_window_PAPR")) {                       /* PAPRs (1 x L-Nfft+1) = f(Tx_OFDM_Signal, Nfft) */
+        NEED(2);
+        size_t n = mxGetNumberOfElements(A(0)), i;
+        int W = (int)mxGetScalar(A(1));
+        if (W < 1 || (size_t)W > n) fail("ofdm:calculate_window_PAPR:size", "Nfft must be in 1..length(signal)");
+        size_t no = n - (size_t)W + 1;
+        void* d = devbuf(rsz() * no);
+        void* h = hostbuf(rsz() * no);
+        chk(ofdm_window_papr(g_ctx, to_dev_complex(A(0), n), 1, (int64_t)n, W, d), op);
+        chk(ofdm_d2h(g_ctx, h, d, rsz() * no), "d2h");
+        mxArray* o = mxCreateDoubleMatrix(1, no, mxREAL);
+        for (i = 0; i < no; ++i) real_data(o)[i] = g_prec == OFDM_PREC_F64 ? ((double*)h)[i] : (double)((float*)h)[i];
+        OUT(0, o);
+    } else if (!strcmp(op, "calculateCCDF")) {                               /* [PAPR_ccdf, CCDF] = f(PAPR_values): column vectors as ecdf */
+        NEED(1);
+        size_t n = mxGetNumberOfElements(A(0)), i;
+        if (n < 1) fail("ofdm:calculateCCDF:size", "empty input");
+        void* hv = hostbuf(rsz() * n);
+        for (i = 0; i < n; ++i) { double v = real_data(A(0))[i]; if (g_prec == OFDM_PREC_F64) ((double*)hv)[i] = v; else ((float*)hv)[i] = (float)v; }
+        void* dv = devbuf(rsz() * n);
+        void* dx = devbuf(rsz() * (n + 1));
+        void* dc = devbuf(rsz() * (n + 1));
+        int64_t* dn = (int64_t*)devbuf(8);
+        int64_t k = 0;
+        chk(ofdm_h2d(g_ctx, dv, hv, rsz() * n), "h2d");
+        chk(ofdm_ccdf(g_ctx, dv, (int64_t)n, dx, dc, dn), op);
+        chk(ofdm_d2h(g_ctx, &k, dn, 8), "d2h");
+        void* hx = hostbuf(rsz() * (size_t)k);
+        void* hc = hostbuf(rsz() * (size_t)k);
+        chk(ofdm_d2h(g_ctx, hx, dx, rsz() * (size_t)k), "d2h");
+        chk(ofdm_d2h(g_ctx, hc, dc, rsz() * (size_t)k), "d2h");
+        mxArray* ox = mxCreateDoubleMatrix((size_t)k, 1, mxREAL);
+        mxArray* oc = mxCreateDoubleMatrix((size_t)k, 1, mxREAL);
+        for (i = 0; i < (size_t)k; ++i) {
+            real_data(ox)[i] = g_prec == OFDM_PREC_F64 ? ((double*)hx)[i] : (double)((float*)hx)[i];
+            real_data(oc)[i] = g_prec == OFDM_PREC_F64 ? ((double*)hc)[i] : (double)((float*)hc)[i];
+        }
+        OUT(0, ox);
+        OUT(1, oc);
     } else {
         fail("ofdm:arg:op", "unknown operation");
     }

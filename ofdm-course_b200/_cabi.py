@@ -72,6 +72,9 @@ SIGNATURES = {
     "ofdm_mp": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp]),
     "ofdm_ber_count": (i32, [vp, vp, vp, i64, vp]),
     "ofdm_mer": (i32, [vp, vp, i64, i32, vp]),
+    "ofdm_papr": (i32, [vp, vp, i64, i64, vp]),
+    "ofdm_window_papr": (i32, [vp, vp, i64, i64, i32, vp]),
+    "ofdm_ccdf": (i32, [vp, vp, i64, vp, vp, vp]),
     "ofdm_tx_chain": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp]),
     "ofdm_channel_t5": (i32, [vp, vp, i64, i64, vp, vp, u64, i64, vp, i32, vp]),
     "ofdm_rx_chain_t5": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, vp, dbl]),

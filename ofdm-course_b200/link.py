@@ -409,6 +409,32 @@ class Context:
         self._chk(self.lib.ofdm_mer(self.h, self.p(iq_dev), iq_dev.numel(), CONSTELLATIONS[str(constellation)], self.p(sums)))
         return sums
 
+    # ---------------------------------------------------------------- PAPR / CCDF
+    def papr(self, x_dev):
+        """`calculatePAPR.m:2-11` per stream (x_dev: B x L) -> B doubles (dB)."""
+        B, L = x_dev.shape
+        out = torch.empty(B, dtype=torch.float64, device=self.device)
+        self._chk(self.lib.ofdm_papr(self.h, self.p(x_dev), B, L, self.p(out)))
+        return out
+
+    def window_papr(self, x_dev, Nfft):
+        """`calculate_window_PAPR.m:2-15` per stream -> B x (L - Nfft + 1)."""
+        B, L = x_dev.shape
+        out = torch.empty((B, L - Nfft + 1), dtype=self.rdtype, device=self.device)
+        self._chk(self.lib.ofdm_window_papr(self.h, self.p(x_dev), B, L, int(Nfft), self.p(out)))
+        return out
+
+    def ccdf(self, values_dev):
+        """`calculateCCDF.m:2-6`: (PAPR_ccdf, CCDF) with ecdf's leading duplicate of the minimum."""
+        v = values_dev.reshape(-1).contiguous()
+        n = v.numel()
+        xs = torch.empty(n + 1, dtype=v.dtype, device=self.device)
+        cc = torch.empty(n + 1, dtype=v.dtype, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._chk(self.lib.ofdm_ccdf(self.h, self.p(v), n, self.p(xs), self.p(cc), self.p(cnt)))
+        k = int(cnt.item())
+        return xs[:k], cc[:k]
+
     # ---------------------------------------------------------------- fused chains
     def tx_chain(self, lp, bits_dev, B):
         out = self.empty_c(B, lp.S, lp.Nfft + lp.Tg)
@@ -734,3 +760,22 @@ def MER_func(IQ_RX, Constellation, precision="f32"):
     c = _ctx(precision)
     s = c.mer(c.cplx(np.asarray(IQ_RX).ravel()), Constellation).cpu().numpy()
     return 10 * np.log10(s[0] / s[1])
+
+
+def calculatePAPR(OFDM_signal, precision="f32"):
+    """`Task 5/calculatePAPR.m:2` -> PAPR in dB"""
+    c = _ctx(precision)
+    return float(c.papr(c.cplx(np.asarray(OFDM_signal).ravel())[None])[0].item())
+
+
+def calculate_window_PAPR(Tx_OFDM_Signal, Nfft, precision="f32"):
+    """`Task 5/calculate_window_PAPR.m:2` -> PAPRs (1 x L-Nfft+1)"""
+    c = _ctx(precision)
+    return c.window_papr(c.cplx(np.asarray(Tx_OFDM_Signal).ravel())[None], int(Nfft)).cpu().numpy().astype(np.float64)
+
+
+def calculateCCDF(PAPR_values, precision="f32"):
+    """`Task 5/calculateCCDF.m:2` -> (PAPR_ccdf, CCDF), column vectors as MATLAB's ecdf returns them"""
+    c = _ctx(precision)
+    xs, cc = c.ccdf(c.real(np.asarray(PAPR_values, dtype=np.float64).ravel(), c.rdtype))
+    return xs.cpu().numpy().astype(np.float64)[:, None], cc.cpu().numpy().astype(np.float64)[:, None]

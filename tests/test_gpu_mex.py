@@ -106,6 +106,19 @@ def test_mex_bits_and_mapping(mex):
     assert abs(mex.call("MER_func", iq.ravel() + 0.01, "16QAM")[0, 0] - O.MER_func(iq_ref + 0.01, "16QAM")) < 1e-3
 
 
+def test_mex_papr_and_ccdf(mex):
+    """calculatePAPR / calculate_window_PAPR / calculateCCDF through the gateway (`Task 2/Main_model_Task_2.m:72-82`)."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(3000) + 1j * rng.standard_normal(3000)
+    assert abs(mex.call("calculatePAPR", x)[0, 0] - O.calculatePAPR(x)) < 1e-4
+    w = mex.call("calculate_window_PAPR", x, 256.0)
+    assert w.shape == (1, 3000 - 256 + 1) and np.max(np.abs(w.ravel() - O.calculate_window_PAPR(x, 256))) < 1e-4
+    xs, cc = mex.call("calculateCCDF", np.round(w, 1), nout=2)
+    rx, rc = O.calculateCCDF(np.round(w, 1).astype(np.float32).astype(np.float64))
+    assert xs.shape == (rx.size, 1) and cc.shape == (rx.size, 1)
+    assert np.max(np.abs(xs.ravel() - rx)) < 1e-6 and np.max(np.abs(cc.ravel() - rc)) < 1e-6
+
+
 def test_mex_ofdm_and_channel_estimation(mex):
     rng = np.random.default_rng(2)
     p = OC.params_task5(comb=16)

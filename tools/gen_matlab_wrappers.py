@@ -29,6 +29,9 @@ W = [
     ("MP_estimate", "[H_MP,h_impulse_est]", "Y, sensing_matrix, Nfft, dominant_taps", "Task 5/MP_estimate.m:2"),
     ("BER_func", "[BER]", "Bit_Tx, Bit_Rx", "Task 5/BER_func.m:1"),
     ("MER_func", "[MER]", "IQ_RX, Constellation", "Task 5/MER_func.m:1"),
+    ("calculatePAPR", "PAPR", "OFDM_signal", "Task 5/calculatePAPR.m:2"),
+    ("calculate_window_PAPR", "PAPRs", "Tx_OFDM_Signal, Nfft", "Task 5/calculate_window_PAPR.m:2"),
+    ("calculateCCDF", "[PAPR_ccdf, CCDF]", "PAPR_values", "Task 5/calculateCCDF.m:2"),
 ]
 NOTES = {
     "Noise": "%   Optional third argument: an L-by-2 matrix of unit normals (column 1 real part, column 2 imaginary\n"
