@@ -264,10 +264,9 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 uint32_t nib;
                 if (QAM16) nib = demap16_nib<NEAR>(e.x, e.y, two_a, &margin);
                 else nib = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
-                if (dr != 0xFFFFu) {
-                    sp[dr] = (uint8_t)nib;
-                    if (NEAR && margin < near_eps) ++nears;
-                }
+                // predicated byte store (the decision itself is computed for every lane: no divergent region)
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0xFFFF;\n\t@p st.shared.u8 [%1], %2;\n\t}" ::"r"(dr), "r"(smem_u32(sp) + dr), "r"(nib) : "memory");
+                if (NEAR && dr != 0xFFFFu && margin < near_eps) ++nears;
             }
         }
         // ---- frame complete: pack, DeScrambler, compare (reference words were prefetched before pass C's tail)
