@@ -243,15 +243,14 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                 if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cmul(Y[c], pinv[pi]); }
             }
             __syncthreads();
-            plan_apply(plan, yk, dk, Hinv);   // Hinv temporarily holds H (nq = Nc entries)
-            __syncthreads();
-            for (int k = tid; k < p.Nc; k += FX_THREADS) {
-                float2 h = Hinv[k];
-                if (Hout) stg_once(Hout + b * p.Nc + k, h);
-                float dd = h.x * h.x + h.y * h.y;
-                Hinv[k] = make_float2(h.x / dd, -h.y / dd);
-            }
-            __syncthreads();
+            // Hermite stage emits carrier q = tid + 256 u from thread tid -- exactly the entries this thread equalises
+            // with, so 1/H goes straight to its slot and no barrier is needed before the equaliser
+            float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
+            plan_apply_fn<float>(plan, yk, dk, [&](int q, float2 h) {
+                if (Hrow) stg_once(Hrow + q, h);
+                const float dd = h.x * h.x + h.y * h.y;
+                Hinv[q] = make_float2(h.x / dd, -h.y / dd);
+            });
         }
         // ---- equalise + decide (branch-free per carrier; pilots / unused carriers skip the store)
         {
