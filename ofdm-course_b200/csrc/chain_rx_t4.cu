@@ -334,14 +334,23 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         const int tg = p.time_desync ? tg_pos[b] : 0;
         const double fo = p.freq_desync ? freq_off[b] : 0.0;
         const bool tshift = p.time_desync != 0;
-        // ---- remove_IFO: first bin of |fft(y3(Nfft+1:2*Nfft))| above 0.77 (`remove_IFO.m:5-8`), warp 0
+        // ---- remove_IFO (`remove_IFO.m:5-8`) overlapped with the first round of symbols.
+        // Derotating by c = fo + ifo cycles per Nfft samples is derotating by fo, shifting the spectrum by ifo bins and
+        // a per-symbol phase: X_c[k] = exp(-2j*pi*c*n0/N) * X_fo[(k + ifo) mod N].  So while warp 0 runs the IFO search
+        // (first bin of |fft(y3(Nfft+1:2*Nfft))| above 0.77; the window's constant phase exp(-2j*pi*fo) does not change
+        // magnitudes and is skipped), warps 1..7 already transform symbols 0..6 with the fo-only table -- unpruned, since
+        // the shift is not known yet -- and pick their bins once ifo is published.
         int ifo = 0;
+        const int n_first = p.freq_desync ? min(NW - 1, p.S) : 0;
         if (p.freq_desync) {
+            for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(fo * (double)i / N);
+            __syncthreads();
+            float2 v[32];
+            const int s1 = warp - 1;
             if (warp == 0) {
-                float2 v[32];
                 load_window(r, (int64_t)N, tg, tshift, v);
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], rot_from_cycles(fo * (double)(N + 32 * n1 + lane) / N));
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], wtab[32 * n1 + lane]);
                 pass_a(v);
                 fft32<32>(v);
                 int first = 0x7fffffff;
@@ -352,20 +361,39 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
                 }
                 first = warp_min(first);
                 if (lane == 0) ifo_s = (first == 0x7fffffff) ? -1 : first;
+            } else if (s1 < n_first) {
+                load_window(r, (int64_t)s1 * SL + p.Tg, tg, tshift, v);
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], wtab[32 * n1 + lane]);
+                pass_a(v);
+                fft32<32>(v);
+#pragma unroll
+                for (int k2 = 0; k2 < 32; ++k2) E[lane + 32 * k2] = v[k2];      // whole spectrum, natural order, in the warp's tile
             }
+        }
+        if (p.freq_desync) {
             __syncthreads();
             ifo = ifo_s;
+            const int s1 = warp - 1;
+            if (warp > 0 && s1 < n_first) {
+                const double c1 = fo + (ifo > 0 ? ifo : 0);
+                const float2 rs = rot_from_cycles(c1 * (double)((int64_t)s1 * SL + p.Tg) / N);
+                const int sh = ifo > 0 ? ifo : 0;
+                for (int k = lane; k < p.Nc; k += 32) Ysc[(int64_t)s1 * p.Nc + k] = cmul(E[(k + sh) & (N - 1)], rs);
+                for (int q = lane; q < p.Np; q += 32) Yp[s1 * p.Np + q] = cmul(E[(p.pil0[q] + sh) & (N - 1)], rs);
+                __syncwarp();
+            }
         }
         if (tid == 0 && ifo_out) ifo_out[b] = ifo;
         const double c = fo + (ifo > 0 ? ifo : 0);   // total derotation in cycles per Nfft samples
         if (p.freq_desync) {
-            for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(c * (double)i / N);
+            __syncthreads();                          // every warp is done with the fo-only table
+            if (ifo > 0) for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(c * (double)i / N);
             for (int s = tid; s < p.S; s += T4_THREADS) rot_s[s] = rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / N);
         }
         __syncthreads();
         // ---- OFDM_demodulator, one warp per symbol; park the useful bins (rotated), keep the pilots
-        // (warp 0 spent a transform on the IFO search: the deal starts at warp 1 so that it gets the short share)
-        for (int s = (warp + NW - 1) % NW; s < p.S; s += NW) {
+        for (int s = n_first + warp; s < p.S; s += NW) {
             float2 v[32];
             load_window(r, (int64_t)s * SL + p.Tg, tg, tshift, v);
             if (p.freq_desync) {
