@@ -53,6 +53,48 @@ template <int N> __device__ __forceinline__ void block_sum_vec(double (&v)[N], d
 }
 
 #define TS_MAXK 16
+static_assert(TC_TOP == TS_THREADS / 32, "one warp re-scores one screened candidate");
+
+// Hermitian positive (semi-)definite k x k solve G x = g in double by ONE WARP (all 32 lanes call; k <= TS_MAXK):
+// lane i owns row i.  Column j of the factor needs the j previous columns, so the factorisation is k steps of O(j)
+// work per lane instead of thread 0 walking k^3/3 terms alone; both triangular solves are right-looking (the lane
+// that just finished an unknown broadcasts it, the others update their partial sums).  Same operations as
+// chol_solve (pursuit_common.cuh); the backward solve accumulates in the opposite order.
+static __device__ __forceinline__ void chol_solve_warp(int k, const double2 (*G)[TS_MAXK], const double2* g, double2* x, double2 (*Lm)[TS_MAXK]) {
+    const int lane = threadIdx.x & 31;
+    for (int j = 0; j < k; ++j) {
+        if (lane == j) {
+            double s = G[j][j].x;
+            for (int q = 0; q < j; ++q) s -= Lm[j][q].x * Lm[j][q].x + Lm[j][q].y * Lm[j][q].y;
+            Lm[j][j] = make_double2(sqrt(fmax(s, 0.0)), 0.0);
+        }
+        __syncwarp();
+        const double dj = Lm[j][j].x;
+        if (lane > j && lane < k) {
+            double2 a = G[lane][j];
+            for (int q = 0; q < j; ++q) a = a - cmulc(Lm[lane][q], Lm[j][q]);
+            Lm[lane][j] = dj > 0 ? cscale(a, 1.0 / dj) : make_double2(0, 0);
+        }
+        __syncwarp();
+    }
+    double2 a = lane < k ? g[lane] : make_double2(0, 0);
+    for (int i = 0; i < k; ++i) {                  // L z = g
+        const double d = Lm[i][i].x;
+        const double2 mine = d > 0 ? cscale(a, 1.0 / d) : make_double2(0, 0);
+        const double2 zi = make_double2(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i));
+        if (lane == i) a = zi;
+        else if (lane > i && lane < k) a = a - cmul(Lm[lane][i], zi);
+    }
+    for (int i = k - 1; i >= 0; --i) {             // L^H x = z
+        const double d = Lm[i][i].x;
+        const double2 mine = d > 0 ? cscale(a, 1.0 / d) : make_double2(0, 0);
+        const double2 xi = make_double2(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i));
+        if (lane == i) a = xi;
+        else if (lane < i) a = a - cmul(cconj(Lm[i][lane]), xi);
+    }
+    if (lane < k) x[lane] = a;
+    __syncwarp();
+}
 // One OMP iteration for one frame.  Per-frame state lives in global memory between iterations: the selection list,
 // the coefficients, the Gram matrix of the unique selected columns and its right-hand side (both double), and the
 // residual (inside the GEMM's A operand).  The Gram matrix grows by one row per iteration.
@@ -66,7 +108,9 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
     __shared__ float sval[32];
     __shared__ int sidx[32];
     __shared__ int sel[TS_MAXK], uniq[TS_MAXK], ucol[TS_MAXK], umult[TS_MAXK];
-    __shared__ double2 G[PU_MAXK][PU_MAXK], Lm[PU_MAXK][PU_MAXK], grhs[PU_MAXK], xu[PU_MAXK];
+    __shared__ double2 G[TS_MAXK][TS_MAXK], Lm[TS_MAXK][TS_MAXK], grhs[TS_MAXK], xu[TS_MAXK];
+    __shared__ float sc_m[TC_TOP];
+    __shared__ int sc_c[TC_TOP];
     __shared__ int s_col, s_nu, s_new;
     const int64_t f = blockIdx.x;
     const int tid = threadIdx.x;
@@ -82,22 +126,20 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
     {
         const float s0 = cand_score[f * TC_TOP], s3 = cand_score[f * TC_TOP + TC_TOP - 1];
         if (s3 < 0.995f * s0 && s0 > 0.f) {   // TF32 scores are good to ~2e-3: the exact argmax is then inside the top-4
-            int cl[TC_TOP];
-            double acc[2 * TC_TOP];
-#pragma unroll
-            for (int c = 0; c < TC_TOP; ++c) { cl[c] = cand[f * TC_TOP + c]; acc[2 * c] = 0; acc[2 * c + 1] = 0; }
-            for (int i = tid; i < Np; i += TS_THREADS) {
-                const double2 rv = to_d(r[i]);
-#pragma unroll
-                for (int c = 0; c < TC_TOP; ++c) { const double2 t = cmulc(rv, to_d(A[(size_t)cl[c] * Np + i])); acc[2 * c] += t.x; acc[2 * c + 1] += t.y; }   // conj(a) * r
-            }
-            block_sum_vec<2 * TC_TOP>(acc, shred);
+            const int w = tid >> 5, lane = tid & 31;          // warp w scores candidate w
+            const int clw = cand[f * TC_TOP + w];
+            const float2* aw = A + (size_t)clw * Np;
+            double ar = 0, ai = 0;
+            for (int i = lane; i < Np; i += 32) { const double2 t = cmulc(to_d(r[i]), to_d(aw[i])); ar += t.x; ai += t.y; }   // conj(a) * r
+            ar = warp_sum(ar); ai = warp_sum(ai);
+            if (lane == 0) { sc_m[w] = (float)(ar * ar + ai * ai); sc_c[w] = clw; }
+            __syncthreads();
             if (tid == 0) {
                 float best = -CUDART_INF_F; int bi = 0x7fffffff;
 #pragma unroll
                 for (int c = 0; c < TC_TOP; ++c) {
-                    const float m = (float)(acc[2 * c] * acc[2 * c] + acc[2 * c + 1] * acc[2 * c + 1]);
-                    if (m > best || (m == best && cl[c] < bi)) { best = m; bi = cl[c]; }
+                    const float m = sc_m[c];
+                    if (m > best || (m == best && sc_c[c] < bi)) { best = m; bi = sc_c[c]; }
                 }
                 s_col = (bi == 0x7fffffff) ? 0 : bi;
             }
@@ -141,33 +183,29 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
     double2* Gf = G_g + f * (int64_t)K * K;
     double2* rf = rhs_g + f * (int64_t)K;
     // ---- the Gram matrix grows by one row (new unique column only): nu dots + the right-hand side, one reduction
-    if (s_new) {
-        double acc[2 * (TS_MAXK + 1)];
-#pragma unroll
-        for (int k = 0; k < 2 * (TS_MAXK + 1); ++k) acc[k] = 0;
+    if (s_new) {                                        // nu dots with the unique columns (the last one is |a_new|^2) + conj(a_new) * y
+        const int w = tid >> 5, lane = tid & 31;
         const float2* an = A + (size_t)col * Np;
-        for (int i = tid; i < Np; i += TS_THREADS) {
-            const double2 av = to_d(an[i]);
-#pragma unroll
-            for (int q = 0; q < TS_MAXK; ++q)
-                if (q < nu) { const double2 t = cmulc(av, to_d(A[(size_t)ucol[q] * Np + i])); acc[2 * q] += t.x; acc[2 * q + 1] += t.y; }   // conj(a_q) * a_new
-            const double2 t = cmulc(to_d(yv[i]), av);                                                                                  // conj(a_new) * y
-            acc[2 * TS_MAXK] += t.x; acc[2 * TS_MAXK + 1] += t.y;
-        }
-        block_sum_vec<2 * (TS_MAXK + 1)>(acc, shred);
-        if (tid == 0) {
-            for (int q = 0; q < nu; ++q) Gf[q * K + (nu - 1)] = make_double2(acc[2 * q], acc[2 * q + 1]);
-            rf[nu - 1] = make_double2(acc[2 * TS_MAXK], acc[2 * TS_MAXK + 1]);
+        for (int j = w; j <= nu; j += TS_THREADS / 32) {
+            const float2* aq = A + (size_t)ucol[j < nu ? j : 0] * Np;
+            double ar = 0, ai = 0;
+            for (int i = lane; i < Np; i += 32) {
+                const double2 av = to_d(an[i]);
+                const double2 t = j < nu ? cmulc(av, to_d(aq[i])) : cmulc(to_d(yv[i]), av);   // conj(a_q) * a_new | conj(a_new) * y
+                ar += t.x; ai += t.y;
+            }
+            ar = warp_sum(ar); ai = warp_sum(ai);
+            if (lane == 0) { if (j < nu) Gf[j * K + (nu - 1)] = make_double2(ar, ai); else rf[nu - 1] = make_double2(ar, ai); }
         }
         __syncthreads();
     }
     if (tid < nu * nu) { const int q = tid / nu, j = tid % nu; G[q][j] = (q <= j) ? Gf[q * K + j] : cconj(Gf[j * K + q]); }
     if (tid < nu) grhs[tid] = rf[tid];
     __syncthreads();
-    if (tid == 0) {
-        chol_solve(nu, G, grhs, xu, Lm);                // x = pinv(A_sel) * y on the unique columns
-        for (int q = 0; q < nsel; ++q) { double2 v = cscale(xu[uniq[q]], 1.0 / (double)umult[uniq[q]]); xs_g[f * K + q] = make_float2((float)v.x, (float)v.y); }
-        sel_g[f * K + nsel - 1] = col;
+    if (tid < 32) {
+        chol_solve_warp(nu, G, grhs, xu, Lm);           // x = pinv(A_sel) * y on the unique columns
+        if (tid < nsel) { const double2 v = cscale(xu[uniq[tid]], 1.0 / (double)umult[uniq[tid]]); xs_g[f * K + tid] = make_float2((float)v.x, (float)v.y); }
+        if (tid == 0) sel_g[f * K + nsel - 1] = col;
     }
     __syncthreads();
     // ---- residue = y - A*x and the stopping rule (`OMP_estimate.m:18-22`)
