@@ -255,12 +255,34 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_finish_kernel(const int32_t
             hb[i] = v;
         }
     }
-    if (Hout)
-        for (int m = tid; m < Nfft; m += TS_THREADS) {
-            float ar = 0, ai = 0;
-            for (int u = 0; u < nu; ++u) { float2 w = tw[(m * ucol[u]) & Nmask]; float2 v = hval[u]; ar += v.x * w.x - v.y * w.y; ai += v.x * w.y + v.y * w.x; }
-            Hout[f * (int64_t)Nfft + m] = make_float2(ar, ai);
+    if (Hout) {
+        // H(m) = sum_u h_u W^{c_u m}.  With m = 64 a + b the twiddle is W^{64 c a} * W^{c b}: two 64-entry rows per
+        // selected tap, read once from the table into shared memory (exact entries), instead of nu scattered table
+        // reads per output bin.  (Nfft % 64 == 0 is required; other sizes take the direct form.)
+        __shared__ float2 t_hi[TS_MAXK][64], t_lo[TS_MAXK][64];
+        if ((Nfft & 63) == 0) {
+            for (int e = tid; e < nu * 64; e += TS_THREADS) {
+                const int u = e >> 6, j = e & 63;
+                const float2 v = hval[u];
+                const float2 w = tw[(64 * j * ucol[u]) & Nmask];
+                t_hi[u][j] = make_float2(v.x * w.x - v.y * w.y, v.x * w.y + v.y * w.x);       // h_u * W^{64 c a}
+                t_lo[u][j] = tw[(j * ucol[u]) & Nmask];
+            }
+            __syncthreads();
+            for (int m = tid; m < Nfft; m += TS_THREADS) {
+                const int a = m >> 6, bq = m & 63;
+                float ar = 0, ai = 0;
+                for (int u = 0; u < nu; ++u) { const float2 x = t_hi[u][a], w = t_lo[u][bq]; ar += x.x * w.x - x.y * w.y; ai += x.x * w.y + x.y * w.x; }
+                Hout[f * (int64_t)Nfft + m] = make_float2(ar, ai);
+            }
+        } else {
+            for (int m = tid; m < Nfft; m += TS_THREADS) {
+                float ar = 0, ai = 0;
+                for (int u = 0; u < nu; ++u) { float2 w = tw[(m * ucol[u]) & Nmask]; float2 v = hval[u]; ar += v.x * w.x - v.y * w.y; ai += v.x * w.y + v.y * w.x; }
+                Hout[f * (int64_t)Nfft + m] = make_float2(ar, ai);
+            }
         }
+    }
 }
 
 // returns OFDM_OK and sets *handled when the tensor-core path ran
