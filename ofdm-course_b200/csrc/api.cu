@@ -75,6 +75,15 @@ extern "C" int ofdm_ctx_create(ofdm_ctx** out, int device, int precision) {
     ctx->precision = precision;
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return OFDM_ERR_CUDA; }
+    {   // Stream-ordered temporaries (cudaMallocAsync in the fused chains) are multi-GB: keep freed blocks in the pool
+        // instead of returning them to the driver at every synchronisation (the default release threshold is 0).
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~(uint64_t)0;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     ctx->own_stream = true;
     for (int i = 0; i < 2; ++i) cudaStreamCreateWithFlags(&ctx->copy_stream[i], cudaStreamNonBlocking);
     for (int i = 0; i < 4; ++i) cudaEventCreateWithFlags(&ctx->ev[i], cudaEventDisableTiming);
