@@ -61,18 +61,23 @@ template <typename T>
 __global__ void add_noise_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const double* __restrict__ snr_db,
                                  const double* __restrict__ power_sum, const T* __restrict__ normals, uint64_t seed,
                                  int64_t first_stream, cx<T>* __restrict__ out, double* __restrict__ nvar) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * L) return;
-    int64_t b = i / L, n = i - b * L;
-    double P = power_sum[b] / (double)L;
-    double np = P / pow(10.0, snr_db[b] / 10.0);
-    T sigma = (T)sqrt(np / 2);
-    T g1, g2;
-    if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
-    else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
-    cx<T> v = in[i];
-    out[i] = mk<T>(v.x + sigma * g1, v.y + sigma * g2);
-    if (nvar && n == 0) nvar[b] = sqrt(np);
+    __shared__ T sigma_s;
+    const int64_t b = blockIdx.x;
+    if (threadIdx.x == 0) {                          // NoisePower = P / 10^(SNR/10), once per CTA (`Noise.m:3-5`)
+        const double P = power_sum[b] / (double)L;
+        const double np = P / pow(10.0, snr_db[b] / 10.0);
+        sigma_s = (T)sqrt(np / 2);
+        if (nvar && blockIdx.y == 0) nvar[b] = sqrt(np);
+    }
+    __syncthreads();
+    const T sigma = sigma_s;
+    for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
+        T g1, g2;
+        if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
+        else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
+        const cx<T> v = in[b * L + n];
+        out[b * L + n] = mk<T>(v.x + sigma * g1, v.y + sigma * g2);
+    }
 }
 extern "C" int ofdm_add_noise(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const double* snr_db, const void* normals,
                               uint64_t seed, int64_t first_stream_id, void* out, double* nvar) {
@@ -86,8 +91,8 @@ extern "C" int ofdm_add_noise(ofdm_ctx* ctx, const void* in, int64_t B, int64_t 
     DISPATCH_T(ctx, {
         stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, psum);
         ctx->launches++;
-        add_noise_kernel<T><<<(unsigned)cdiv64(B * L, 256), 256, 0, ctx->stream>>>((const cx<T>*)in, B, L, snr_db, psum, (const T*)normals, seed,
-                                                                                    first_stream_id, (cx<T>*)out, nvar);
+        add_noise_kernel<T><<<dim3((unsigned)B, (unsigned)std::min<int64_t>(cdiv64(L, 256 * 4), 256)), 256, 0, ctx->stream>>>(
+            (const cx<T>*)in, B, L, snr_db, psum, (const T*)normals, seed, first_stream_id, (cx<T>*)out, nvar);
     });
     LAUNCH_CHECK(ctx);
     return OFDM_OK;
@@ -128,18 +133,24 @@ template <typename T>
 __global__ void fir_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const cx<T>* __restrict__ h, int D, int per_stream,
                            cx<T>* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* hs = (cx<T>*)smem_raw;
+    cx<T>* hv = (cx<T>*)smem_raw;                   // non-zero taps in ascending delay (sparse channels: 3-6 of 11-26)
+    int* hd = (int*)(hv + D);
+    __shared__ int nnz_s;
     const int64_t b = blockIdx.x;
     const cx<T>* hb = per_stream ? h + b * D : h;
-    for (int d = threadIdx.x; d < D; d += blockDim.x) hs[d] = hb[d];
+    if (threadIdx.x == 0) {
+        int k = 0;
+        for (int d = 0; d < D; ++d) { const cx<T> t = hb[d]; if (t.x != (T)0 || t.y != (T)0) { hv[k] = t; hd[k] = d; ++k; } }
+        nnz_s = k;
+    }
     __syncthreads();
+    const int nnz = nnz_s;
+    const cx<T>* x = in + b * L;
     for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
         cx<T> acc = mk<T>(0, 0);
-        const cx<T>* x = in + b * L;
-        int dmax = (int)min((int64_t)D - 1, n);
-        for (int d = 0; d <= dmax; ++d) {
-            cx<T> t = hs[d];
-            if (t.x != (T)0 || t.y != (T)0) acc = acc + cmul(x[n - d], t);   // sparse taps: skip exact zeros
+        for (int t = 0; t < nnz; ++t) {
+            const int d = hd[t];
+            if ((int64_t)d <= n) acc = acc + cmul(x[n - d], hv[t]);
         }
         out[b * L + n] = acc;
     }
@@ -151,19 +162,90 @@ extern "C" int ofdm_apply_fir(ofdm_ctx* ctx, const void* in, int64_t B, int64_t 
     if (B * L == 0) return OFDM_OK;
     int bx = (int)std::min<int64_t>(cdiv64(L, 256), 256);
     DISPATCH_T(ctx, {
-        fir_kernel<T><<<dim3((unsigned)B, bx), 256, sizeof(cx<T>) * D, ctx->stream>>>((const cx<T>*)in, B, L, (const cx<T>*)h, D, per_stream, (cx<T>*)out);
+        fir_kernel<T><<<dim3((unsigned)B, bx), 256, (sizeof(cx<T>) + sizeof(int)) * D, ctx->stream>>>((const cx<T>*)in, B, L, (const cx<T>*)h, D, per_stream, (cx<T>*)out);
     });
     LAUNCH_CHECK(ctx);
     return OFDM_OK;
 }
 
 // ---- fused Task-5 channel: AWGN then FIR (`Task 5/Main_model_Task_5.m:108,123-127`).
+// One CTA produces CH_TILE consecutive output samples of one stream: the noisy samples it needs (tile + D-1 of
+// history) are formed in shared memory -- x + sigma*(g1 + i g2), the Philox normals are addressed by sample index,
+// so the history of a tile is regenerated, not exchanged -- and filtered from there with the NON-ZERO taps only
+// (ordered list built per CTA; the course's channels have 3-6 taps over 11-26 delays).  Same operations in the
+// same order as add_noise_kernel followed by fir_kernel, without the 8 B/sample round trip in between.
+#define CH_TILE 2048
+#define CH_MAXD 1024
+template <typename T>
+__global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict__ in, int64_t L, const double* __restrict__ snr_db,
+                                                         const double* __restrict__ power_sum, const T* __restrict__ normals, uint64_t seed,
+                                                         int64_t first_stream, const cx<T>* __restrict__ h, int D, cx<T>* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sn = (cx<T>*)smem_raw;                   // CH_TILE + D - 1 noisy samples
+    cx<T>* hv = sn + CH_TILE + D - 1;               // non-zero taps, ascending delay
+    int* hd = (int*)(hv + D);
+    __shared__ T sigma_s;
+    __shared__ int nnz_s;
+    const int64_t b = blockIdx.x;
+    const int64_t n0 = (int64_t)blockIdx.y * CH_TILE;
+    if (threadIdx.x == 0) {
+        const double P = power_sum[b] / (double)L;
+        sigma_s = (T)sqrt(P / pow(10.0, snr_db[b] / 10.0) / 2);
+        int k = 0;
+        for (int d = 0; d < D; ++d) { const cx<T> t = h[d]; if (t.x != (T)0 || t.y != (T)0) { hv[k] = t; hd[k] = d; ++k; } }
+        nnz_s = k;
+    }
+    __syncthreads();
+    const T sigma = sigma_s;
+    const int nnz = nnz_s;
+    for (int j = threadIdx.x; j < CH_TILE + D - 1; j += 256) {
+        const int64_t n = n0 - (D - 1) + j;
+        cx<T> v = mk<T>(0, 0);
+        if (n >= 0 && n < L) {
+            T g1, g2;
+            if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
+            else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
+            const cx<T> x = in[b * L + n];
+            v = mk<T>(x.x + sigma * g1, x.y + sigma * g2);
+        }
+        sn[j] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < CH_TILE; j += 256) {
+        const int64_t n = n0 + j;
+        if (n >= L) break;
+        cx<T> acc = mk<T>(0, 0);
+        for (int t = 0; t < nnz; ++t) {
+            const int d = hd[t];
+            if ((int64_t)d <= n) acc = acc + cmul(sn[j + D - 1 - d], hv[t]);
+        }
+        out[b * L + n] = acc;
+    }
+}
+
 extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const void* normals,
                                uint64_t seed, int64_t first_stream_id, const void* h, int D, void* rx) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, tx && rx && B >= 0 && L >= 0, "bad argument");
     if (B * L == 0) return OFDM_OK;
     size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
+    if (snr_db && h && D >= 1 && D <= CH_MAXD && tx != rx) {
+        double* psum = (double*)ctx_scratch(ctx, sizeof(double) * B);
+        REQUIRE(ctx, psum != nullptr, "scratch allocation failed");
+        CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
+        const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
+        DISPATCH_T(ctx, {
+            stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)tx, L, psum);
+            ctx->launches++;
+            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + 2 * D - 1) + sizeof(int) * (size_t)D;
+            auto k = channel_t5_kernel<T>;
+            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<dim3((unsigned)B, (unsigned)cdiv64(L, CH_TILE)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, snr_db, psum, (const T*)normals, seed, first_stream_id,
+                                                                                             (const cx<T>*)h, D, (cx<T>*)rx);
+        });
+        LAUNCH_CHECK(ctx);
+        return OFDM_OK;
+    }
     if (snr_db && h) {
         // noise must precede the filter; stage the noisy stream in a second buffer region
         void* tmp = nullptr;
