@@ -4,6 +4,7 @@
 // The Nfft = 4096 / N_carrier <= 1024 fast path of the RX chain lives in chain_rx4096.cu.
 #include "fft.cuh"
 #include "interp.cuh"
+#include "fft_reg.cuh"
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
 #define SLOT_ZERO (-2147483647 - 1)
@@ -128,10 +129,157 @@ __global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, cons
     }
 }
 
+// ---- TX fast path, Nfft = 4096, N_carrier <= 1024, FP32: the modulator's IFFT in registers.
+// ifft(X) = conj(fft(conj(X))) / N, and with k = 256 m1 + t only m1 < 4 carries energy (`OFDM_map_carriers.m:3-7` fills
+// rows 1..N_carrier), so the forward structure of the RX kernel is reused with the pruning on the INPUT side:
+//   pass A  thread t: the four conjugated carriers t + 256 m1 -> 16-point DFT over m1 (12 zero inputs fold away at
+//           compile time) x W4096^{t q1} -> [256 q1 + t]
+//   pass B  thread (q1, m3): DFT over m2 x W256^{m3 q2} -> [258 q1 + 16 q2 + m3]
+//   pass C  thread (q1 = t&15, q2 = t>>4): DFT over m3 -> samples n = t + 256 q3, q3 = 0..15: every store of a warp is
+//           one contiguous 256-byte row; rows q3 >= 16 - Tg/256.. also feed the cyclic prefix (`OFDM_modulator.m:7-9`).
+// Carriers are built straight into registers from the scrambled frame (shared-memory bit array, log-depth GF(2)
+// scrambler as in tx_chain_kernel) -- no frequency grid is ever stored.  Two transform buffers alternate, so a
+// symbol costs three block barriers.
+#define TXF_XROW 258
+#define TXF_XBUF 4128
+__global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xb = (float2*)smem_raw;                       // two transform buffers
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint32_t* s0 = (uint32_t*)(xb + 2 * TXF_XBUF);
+    uint32_t* s1 = s0 + fw;
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    float2 ta[16], tb[16];
+#pragma unroll
+    for (int q1 = 0; q1 < 16; ++q1) ta[q1] = p.tw[(tid * q1) & 4095];                 // W4096^{t*q1}
+    {
+        const int m3 = tid & 15;
+#pragma unroll
+        for (int q2 = 0; q2 < 16; ++q2) tb[q2] = p.tw[(16 * m3 * q2) & 4095];         // W256^{m3*q2}
+    }
+    int slot4[4];
+#pragma unroll
+    for (int m1 = 0; m1 < 4; ++m1) slot4[m1] = p.slot[tid + 256 * m1];
+    const float scale = 1.f / 4096.f;
+    int par = 0;
+    for (int f = 0; f < p.frames; ++f) {
+        const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+        __syncthreads();                                   // previous frame's bit array is no longer read
+        for (int w = tid; w < fw; w += CH_THREADS) {
+            uint32_t v = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+            if (w == 0 && p.scramble) v ^= (p.prev0 >> 19) ^ (p.prev0 >> 18);   // fold the register pre-history into the input
+            s0[w] = v;
+        }
+        __syncthreads();
+        uint32_t* cur = s0; uint32_t* nxt = s1;
+        if (p.scramble) {
+            for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
+                for (int w = tid; w < fw; w += CH_THREADS)
+                    nxt[w] = cur[w] ^ sm_get32(cur, 32 * w - sh13, fw) ^ sm_get32(cur, 32 * w - sh14, fw);
+                __syncthreads();
+                uint32_t* t = cur; cur = nxt; nxt = t;
+            }
+        }
+        for (int sf = 0; sf < p.SpF; ++sf) {
+            const int s = f * p.SpF + sf;
+            float2* X = xb + par * TXF_XBUF;
+            par ^= 1;
+            float2 v[16];
+            // ---- carriers of this thread, conjugated (mapping.m:14-21, OFDM_map_carriers.m:3-7)
+#pragma unroll
+            for (int m1 = 0; m1 < 4; ++m1) {
+                const int sl = slot4[m1];
+                float2 c = make_float2(0.f, 0.f);
+                if (sl >= 0) {
+                    const int q = sf * p.Nd + sl;
+                    const uint32_t g = sm_get32(cur, q * p.bps, fw);
+                    int idx = 0;
+                    for (int i = 0; i < p.bps; ++i) idx = (idx << 1) | ((g >> i) & 1u);
+                    c = make_float2(p.con.re[idx], -p.con.im[idx]);
+                } else if (sl != SLOT_ZERO) { const float2 pv = p.pilots[(int64_t)s * p.Np + (-1 - sl)]; c = make_float2(pv.x, -pv.y); }
+                v[m1] = c;
+            }
+#pragma unroll
+            for (int m1 = 4; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
+            // ---- pass A
+            fft16(v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int q1 = c + 4 * d;
+                    float2 x = v[4 * c + d];
+                    if (q1) x = cmul(x, ta[q1]);
+                    X[q1 * 256 + tid] = x;
+                }
+            __syncthreads();
+            // ---- pass B
+            {
+                float2* rp = X + (tid >> 4) * 256 + (tid & 15);
+#pragma unroll
+                for (int m2 = 0; m2 < 16; ++m2) v[m2] = rp[16 * m2];
+                __syncthreads();
+                fft16(v);
+                float2* wp = X + (tid >> 4) * TXF_XROW + (tid & 15);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int q2 = c + 4 * d;
+                        float2 x = v[4 * c + d];
+                        if (q2) x = cmul(x, tb[q2]);
+                        wp[16 * q2] = x;
+                    }
+            }
+            __syncthreads();
+            // ---- pass C (all 16 outputs) + conj/N + cyclic prefix
+            {
+                const float4* rp = reinterpret_cast<const float4*>(X + (tid & 15) * TXF_XROW + (tid >> 4) * 16);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 w = rp[j];
+                    v[2 * j] = make_float2(w.x, w.y);
+                    v[2 * j + 1] = make_float2(w.z, w.w);
+                }
+            }
+            fft16(v);
+            float2* dst = out + (b * p.S + s) * (int64_t)(4096 + p.Tg);
+            const int cp0 = 4096 - p.Tg;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int q3 = c + 4 * d;
+                    const int n = tid + 256 * q3;
+                    const float2 y = make_float2(v[4 * c + d].x * scale, -v[4 * c + d].y * scale);
+                    dst[p.Tg + n] = y;
+                    if (n >= cp0) dst[n - cp0] = y;
+                }
+        }
+    }
+}
+
 extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, bits && time && B >= 0, "bad argument");
     if (B == 0) return OFDM_OK;
+    if (ctx->precision == OFDM_PREC_F32 && lp && lp->Nfft == 4096 && lp->N_carrier <= 1024 && !getenv("OFDM_B200_NO_FAST")) {
+        LinkDev<float> d;
+        int rc = make_linkdev<float>(ctx, lp, d);
+        if (rc) return rc;
+        bool ok = true;                                   // every occupied row must lie in 1..1024
+        for (int i = 0; i < lp->Nd && ok; ++i) ok = lp->data_carriers_host[i] <= 1024;
+        for (int i = 0; i < lp->Np && ok; ++i) ok = lp->pilot_carriers_host[i] <= 1024;
+        const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * ((d.frame_bits + 31) / 32);
+        if (ok && smem <= 110 * 1024) {
+            CUDA_TRY(ctx, cudaFuncSetAttribute(tx4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            tx4096_kernel<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (float2*)time);
+            LAUNCH_CHECK(ctx);
+            return OFDM_OK;
+        }
+    }
     DISPATCH_T(ctx, {
         LinkDev<T> d;
         int rc = make_linkdev<T>(ctx, lp, d);
