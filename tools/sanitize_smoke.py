@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Tiny invocations of the fused kernels for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ofdm_b200 as G  # noqa: E402
+import oracle as O  # noqa: E402
+from oracle import chains as OC  # noqa: E402
+
+ctx = G.Context(0, "f32")
+rng = np.random.default_rng(0)
+# Task-5 shape: TX fast path, fused channel, RX-4096 kernel
+p = OC.params_task5(comb=4)
+lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers, p.pilotCarriers, p.pilotValues)
+B = 3
+bits = ctx.bits(rng.integers(0, 2, B * p.stream_bits).astype(np.uint8))
+h, _ = O.get_MP_channel_resp([[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]], p.Nfft)
+tx = ctx.tx_chain(lp, bits, B)
+rx = ctx.channel_t5(tx, snr_db=20.0, h_dev=ctx.cplx(h), seed=1)
+r5 = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bits, near_eps=1e-3)
+# Task-4 shape: autocorrelation + warp-per-symbol chain
+p4 = OC.params_task4()
+lp4 = ctx.link_params(p4.Nfft, p4.T_Guard, p4.N_carrier, p4.N_symb, p4.Amount_ODFM_SpF, p4.Constellation, p4.dataCarriers, p4.pilotCarriers, p4.pilotValues)
+b4 = rng.integers(0, 2, (2, p4.stream_bits)).astype(np.uint8)
+rx4 = []
+for i, (sto, cfo) in enumerate([(611, 3.3), (900, 0.24)]):
+    t, _, _ = OC.tx_chain(p4, b4[i], fast=True)
+    rx4.append(OC.impair_task4(p4, t, SNR_dB=28, Time_Delay=sto, Freq_Shift=cfo, taps=[[0, 1], [4, .6], [10, .3]], rng=rng))
+r4 = ctx.rx_chain_t4_fused(lp4, ctx.cplx(np.stack(rx4)), tx_bits_dev=ctx.bits(b4.ravel()), near_eps=1e-3, want_H=True)
+# PAPR kernels
+w = ctx.window_papr(tx.reshape(B, -1)[:, :3 * 4608].contiguous(), 4096)
+xs, cc = ctx.ccdf(w.reshape(-1)[:5000].contiguous())
+ctx.sync()
+print("T5 counts", r5["counts"].cpu().numpy(), "T4 counts", r4["counts"].cpu().numpy(), "papr windows", tuple(w.shape), "ccdf points", xs.numel())
