@@ -71,12 +71,22 @@ __global__ void add_noise_kernel(const cx<T>* __restrict__ in, int64_t B, int64_
     }
     __syncthreads();
     const T sigma = sigma_s;
-    for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
-        T g1, g2;
-        if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
-        else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
-        const cx<T> v = in[b * L + n];
-        out[b * L + n] = mk<T>(v.x + sigma * g1, v.y + sigma * g2);
+    if (normals) {
+        for (int64_t n = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; n < L; n += (int64_t)gridDim.y * blockDim.x) {
+            const T g1 = normals[(b * 2) * L + n], g2 = normals[(b * 2 + 1) * L + n];
+            const cx<T> v = in[b * L + n];
+            out[b * L + n] = mk<T>(v.x + sigma * g1, v.y + sigma * g2);
+        }
+    } else {                                         // one Philox call serves two consecutive samples
+        for (int64_t pr = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; 2 * pr < L; pr += (int64_t)gridDim.y * blockDim.x) {
+            float g[4];
+            philox_normal_quad(seed, (uint64_t)(first_stream + b), (uint64_t)pr, g);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t n = 2 * pr + e;
+                if (n < L) { const cx<T> v = in[b * L + n]; out[b * L + n] = mk<T>(v.x + sigma * (T)g[2 * e], v.y + sigma * (T)g[2 * e + 1]); }
+            }
+        }
     }
 }
 extern "C" int ofdm_add_noise(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const double* snr_db, const void* normals,
@@ -198,17 +208,35 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
     __syncthreads();
     const T sigma = sigma_s;
     const int nnz = nnz_s;
-    for (int j = threadIdx.x; j < CH_TILE + D - 1; j += 256) {
-        const int64_t n = n0 - (D - 1) + j;
-        cx<T> v = mk<T>(0, 0);
-        if (n >= 0 && n < L) {
-            T g1, g2;
-            if (normals) { g1 = normals[(b * 2) * L + n]; g2 = normals[(b * 2 + 1) * L + n]; }
-            else { float a, c; philox_normal_pair(seed, (uint64_t)(first_stream + b), (uint64_t)n, a, c); g1 = (T)a; g2 = (T)c; }
-            const cx<T> x = in[b * L + n];
-            v = mk<T>(x.x + sigma * g1, x.y + sigma * g2);
+    const int64_t nlo = n0 - (D - 1);                // first staged sample (may be negative); sn[j] holds sample nlo + j
+    if (normals) {
+        for (int j = threadIdx.x; j < CH_TILE + D - 1; j += 256) {
+            const int64_t n = nlo + j;
+            cx<T> v = mk<T>(0, 0);
+            if (n >= 0 && n < L) {
+                const cx<T> x = in[b * L + n];
+                v = mk<T>(x.x + sigma * normals[(b * 2) * L + n], x.y + sigma * normals[(b * 2 + 1) * L + n]);
+            }
+            sn[j] = v;
         }
-        sn[j] = v;
+    } else {                                         // sample pairs (2 pr, 2 pr + 1): one Philox call each
+        const int64_t pr0 = nlo >= 0 ? nlo >> 1 : -((-nlo + 1) >> 1);           // floor(nlo / 2)
+        const int npairs = (int)(((nlo + CH_TILE + D - 1 + 1) >> 1) - pr0) + 1;
+        for (int q = threadIdx.x; q < npairs; q += 256) {
+            const int64_t pr = pr0 + q;
+            float g[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pr >= 0 && 2 * pr < L) philox_normal_quad(seed, (uint64_t)(first_stream + b), (uint64_t)pr, g);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int64_t n = 2 * pr + e;
+                const int64_t j = n - nlo;
+                if (j >= 0 && j < CH_TILE + D - 1) {
+                    cx<T> v = mk<T>(0, 0);
+                    if (n >= 0 && n < L) { const cx<T> x = in[b * L + n]; v = mk<T>(x.x + sigma * (T)g[2 * e], x.y + sigma * (T)g[2 * e + 1]); }
+                    sn[j] = v;
+                }
+            }
+        }
     }
     __syncthreads();
     for (int j = threadIdx.x; j < CH_TILE; j += 256) {

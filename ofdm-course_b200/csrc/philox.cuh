@@ -15,14 +15,25 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
         k0 += W0; k1 += W1;
     }
 }
-// two independent unit normals for (stream, sample): Box-Muller on two 32-bit uniforms in (0,1]
-__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t stream, uint64_t n, float& g1, float& g2) {
-    uint32_t c[4] = {(uint32_t)n, (uint32_t)(n >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+// Unit normals for a PAIR of samples (2*pair, 2*pair + 1) of a stream from ONE Philox call: the four 32-bit outputs
+// feed two Box-Muller transforms, (g[0], g[1]) = real/imaginary normal of the even sample, (g[2], g[3]) of the odd one.
+__device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t stream, uint64_t pair, float g[4]) {
+    uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    float u1 = ((float)c[0] + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
-    float u2 = (float)c[1] * 2.3283064365386963e-10f;            // [0,1)
-    float r = sqrtf(-2.0f * __logf(u1));
-    float s, co;
-    __sincosf(6.283185307179586f * u2, &s, &co);
-    g1 = r * co; g2 = r * s;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
+        const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;        // [0,1)
+        const float r = sqrtf(-2.0f * __logf(u1));
+        float s, co;
+        __sincosf(6.283185307179586f * u2, &s, &co);
+        g[2 * h] = r * co; g[2 * h + 1] = r * s;
+    }
+}
+// two independent unit normals for (stream, sample n): the half of the pair's quad that belongs to n
+__device__ __forceinline__ void philox_normal_pair(uint64_t seed, uint64_t stream, uint64_t n, float& g1, float& g2) {
+    float g[4];
+    philox_normal_quad(seed, stream, n >> 1, g);
+    g1 = (n & 1) ? g[2] : g[0];
+    g2 = (n & 1) ? g[3] : g[1];
 }
