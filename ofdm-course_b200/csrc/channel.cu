@@ -239,15 +239,23 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < CH_TILE; j += 256) {
-        const int64_t n = n0 + j;
-        if (n >= L) break;
-        cx<T> acc = mk<T>(0, 0);
-        for (int t = 0; t < nnz; ++t) {
-            const int d = hd[t];
-            if ((int64_t)d <= n) acc = acc + cmul(sn[j + D - 1 - d], hv[t]);
-        }
-        out[b * L + n] = acc;
+    // eight outputs per thread; the tap loop is outermost so that a tap is fetched once for all of them (the order of
+    // additions per output is still ascending delay)
+    cx<T> acc[CH_TILE / 256];
+#pragma unroll
+    for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = mk<T>(0, 0);
+    for (int t = 0; t < nnz; ++t) {
+        const int d = hd[t];
+        const cx<T> w = hv[t];
+        const cx<T>* sp = sn + threadIdx.x + D - 1 - d;
+#pragma unroll
+        for (int i = 0; i < CH_TILE / 256; ++i)
+            if ((int64_t)d <= n0 + threadIdx.x + 256 * i) acc[i] = acc[i] + cmul(sp[256 * i], w);
+    }
+#pragma unroll
+    for (int i = 0; i < CH_TILE / 256; ++i) {
+        const int64_t n = n0 + threadIdx.x + 256 * i;
+        if (n < L) out[b * L + n] = acc[i];
     }
 }
 
