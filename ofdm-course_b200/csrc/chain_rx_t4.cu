@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
     __shared__ double red[32];
     __shared__ int red_i[32];
     __shared__ int cnt[T4_THREADS];
-    __shared__ int ifo_s;
+    __shared__ int ifo_s, next_sym;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = T4_THREADS / 32;
     const int M = p.Np * p.S;
@@ -386,14 +386,20 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         }
         if (tid == 0 && ifo_out) ifo_out[b] = ifo;
         const double c = fo + (ifo > 0 ? ifo : 0);   // total derotation in cycles per Nfft samples
+        if (tid == 0) next_sym = n_first;             // published by the barrier(s) below
         if (p.freq_desync) {
             __syncthreads();                          // every warp is done with the fo-only table
             if (ifo > 0) for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(c * (double)i / N);
             for (int s = tid; s < p.S; s += T4_THREADS) rot_s[s] = rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / N);
         }
         __syncthreads();
-        // ---- OFDM_demodulator, one warp per symbol; park the useful bins (rotated), keep the pilots
-        for (int s = n_first + warp; s < p.S; s += NW) {
+        // ---- OFDM_demodulator, one warp per symbol; park the useful bins (rotated), keep the pilots.  Symbols are handed
+        // out through a shared counter: the warps did unequal work in the first round (IFO search / unpruned transforms).
+        for (;;) {
+            int s = 0;
+            if (lane == 0) s = atomicAdd(&next_sym, 1);
+            s = __shfl_sync(0xffffffffu, s, 0);
+            if (s >= p.S) break;
             float2 v[32];
             load_window(r, (int64_t)s * SL + p.Tg, tg, tshift, v);
             if (p.freq_desync) {
