@@ -14,8 +14,9 @@
 #include "fft_reg.cuh"
 
 #define FX_THREADS 256
-#define XROW 258          // pass-B output row stride (k1): +2 pad keeps rows 16-byte aligned and makes pass C's 128-bit reads conflict free
-#define XBUF 4128         // samples per symbol buffer: 15*258 + 256, rounded to 16
+#define XROW 288          // pass-B output row stride (k1): 16 groups (k2) of 16 samples at stride 18
+#define XGRP 18           // ... the two-sample pad per group makes pass C's 128-bit reads conflict free for eight consecutive k2
+#define XBUF 4608         // samples per symbol buffer: 16 rows of 288
 #define SLOT_ZERO (-2147483647 - 1)
 
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
@@ -118,13 +119,26 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     const int64_t n_items = my_streams * p.S;
     const int64_t stream_stride = (int64_t)p.S * symlen;                 // samples per stream
     const float2* rx0 = rx + (int64_t)blockIdx.x * stream_stride + p.Tg; // first symbol of this CTA's first stream
+    // pass-C coordinates of this thread and its carriers kq + 256 c
+    const int k1c = (tid >> 6) + 4 * ((tid >> 3) & 3), k2c = ((tid >> 5) & 1) * 8 + (tid & 7);
+    const int kq = k1c + 16 * k2c;
     // per-thread carrier roles (fixed for the whole kernel): data rank or 0xFFFF, two per register
     uint32_t role01, role23;
+    bool warp_data, warp_pil;
     {
         uint32_t r[4];
+        bool anyd = false, anyp = false;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { int sl = p.slot[tid + 256 * c]; r[c] = (sl >= 0 && tid + 256 * c < p.Nc) ? (uint32_t)sl : 0xFFFFu; }
+        for (int c = 0; c < 4; ++c) {
+            const int sl = p.slot[kq + 256 * c];
+            const bool in = kq + 256 * c < p.Nc;
+            r[c] = (sl >= 0 && in) ? (uint32_t)sl : 0xFFFFu;
+            anyd |= (sl >= 0 && in);
+            anyp |= (sl < 0 && sl != SLOT_ZERO);
+        }
         role01 = r[0] | (r[1] << 16); role23 = r[2] | (r[3] << 16);
+        warp_data = __any_sync(0xffffffffu, anyd);
+        warp_pil = __any_sync(0xffffffffu, anyp);
     }
     if (tid == 0) {
         mbar_init(&bars[0], 1);
@@ -200,13 +214,14 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                     const int k2 = c + 4 * d;
                     float2 x = v[4 * c + d];
                     if (k2) x = cmul(x, tb[k2]);
-                    wp[16 * k2] = x;
+                    wp[XGRP * k2] = x;
                 }
         }
         __syncthreads();
-        // ---- pass C: thread (k1 = tid&15, k2 = tid>>4), DFT over n3, only k3 = 0..3
+        // ---- pass C: thread (k1c, k2c) -- a quarter warp holds eight consecutive k2 of one k1 (conflict-free 128-bit
+        // reads), a warp the four k1 of one residue mod 4 -- DFT over n3, only k3 = 0..3
         {
-            const float4* rp = reinterpret_cast<const float4*>(X + (tid & 15) * XROW + (tid >> 4) * 16);
+            const float4* rp = reinterpret_cast<const float4*>(X + k1c * XROW + k2c * XGRP);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float4 w = rp[j];
@@ -231,41 +246,48 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = ldg_once(tp + FX_THREADS * j);
         }
-        fft16_steps12(v);
-        float2 Y[4];
+        // A warp whose carriers are all pilots (comb layouts: the k1 = 0 mod comb rows) has nothing to do after the
+        // first symbol of a stream: the channel is estimated from symbol 0 only (`LS_CE.m:27-28`).
+        if (warp_data || s == 0) {
+            fft16_steps12(v);
+            float2 Y[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Y[c] = add2(add2(v[4 * c], v[4 * c + 1]), add2(v[4 * c + 2], v[4 * c + 3]));   // carrier tid + 256*c
-        // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
-        if (s == 0) {
+            for (int c = 0; c < 4; ++c) Y[c] = add2(add2(v[4 * c], v[4 * c + 1]), add2(v[4 * c + 2], v[4 * c + 3]));   // carrier kq + 256*c
+            // ---- symbol 0: LS at the pilots, spline to every carrier, keep 1/H
+            if (s == 0) {
+                if (warp_pil) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int sl = slot_s[tid + 256 * c];
-                if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cmul(Y[c], pinv[pi]); }
+                    for (int c = 0; c < 4; ++c) {
+                        const int sl = slot_s[kq + 256 * c];
+                        if (sl < 0 && sl != SLOT_ZERO) { const int pi = -1 - sl; yk[plan.ext_lo + pi] = cmul(Y[c], pinv[pi]); }
+                    }
+                }
+                __syncthreads();
+                // Hermite stage: thread tid emits carrier q = tid + 256 u; 1/H goes to the slot of the thread that equalises it
+                float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
+                plan_apply_fn<float>(plan, yk, dk, [&](int q, float2 h) {
+                    if (Hrow) stg_once(Hrow + q, h);
+                    const float dd = h.x * h.x + h.y * h.y;
+                    const int k1 = q & 15, k2 = (q >> 4) & 15;
+                    Hinv[(((k1 & 3) << 6) | ((k2 >> 3) << 5) | ((k1 >> 2) << 3) | (k2 & 7)) + (q & ~255)] = make_float2(h.x / dd, -h.y / dd);
+                });
+                __syncthreads();
             }
-            __syncthreads();
-            // Hermite stage emits carrier q = tid + 256 u from thread tid -- exactly the entries this thread equalises
-            // with, so 1/H goes straight to its slot and no barrier is needed before the equaliser
-            float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
-            plan_apply_fn<float>(plan, yk, dk, [&](int q, float2 h) {
-                if (Hrow) stg_once(Hrow + q, h);
-                const float dd = h.x * h.x + h.y * h.y;
-                Hinv[q] = make_float2(h.x / dd, -h.y / dd);
-            });
-        }
-        // ---- equalise + decide (branch-free per carrier; pilots / unused carriers skip the store)
-        {
-            uint8_t* sp = symidx + sfNd;
+            // ---- equalise + decide (branch-free per carrier; pilots / unused carriers skip the store)
+            if (warp_data) {
+                uint8_t* sp = symidx + sfNd;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const uint32_t dr = ((c < 2 ? role01 : role23) >> (16 * (c & 1))) & 0xFFFFu;
-                const float2 e = cmul(Y[c], Hinv[tid + 256 * c]);
-                float margin = 1.f;
-                uint32_t nib;
-                if (QAM16) nib = demap16_nib<NEAR>(e.x, e.y, two_a, &margin);
-                else nib = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
-                // predicated byte store (the decision itself is computed for every lane: no divergent region)
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0xFFFF;\n\t@p st.shared.u8 [%1], %2;\n\t}" ::"r"(dr), "r"(smem_u32(sp) + dr), "r"(nib) : "memory");
-                if (NEAR && dr != 0xFFFFu && margin < near_eps) ++nears;
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t dr = ((c < 2 ? role01 : role23) >> (16 * (c & 1))) & 0xFFFFu;
+                    const float2 e = cmul(Y[c], Hinv[tid + 256 * c]);
+                    float margin = 1.f;
+                    uint32_t nib;
+                    if (QAM16) nib = demap16_nib<NEAR>(e.x, e.y, two_a, &margin);
+                    else nib = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                    // predicated byte store (the decision itself is computed for every lane: no divergent region)
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, 0xFFFF;\n\t@p st.shared.u8 [%1], %2;\n\t}" ::"r"(dr), "r"(smem_u32(sp) + dr), "r"(nib) : "memory");
+                    if (NEAR && dr != 0xFFFFu && margin < near_eps) ++nears;
+                }
             }
         }
         // ---- frame complete: pack, DeScrambler, compare (reference words were prefetched before pass C's tail)
