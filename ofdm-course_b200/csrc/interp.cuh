@@ -22,8 +22,9 @@ template <typename T> static inline PlanDev<T> plan_dev(const InterpPlan* p) {
 // d: shared scratch, n_knots entries.  emit(q, value) receives the nq interpolated values.  Block-cooperative,
 // two barriers: the extrapolated end knots (`interpolate.m:7-16`) are produced by two threads *during* the
 // derivative stage, whose operator was folded on the host so that it never reads them.
-template <typename T, typename Emit>
-__device__ __forceinline__ void plan_apply_fn(const PlanDev<T>& p, cx<T>* y, cx<T>* d, Emit emit) {
+// Stage 1 of plan_apply_fn: edge extension + derivative operator (d = Band * y).  A block barrier must separate it from stage 2.
+template <typename T>
+__device__ __forceinline__ void plan_band_stage(const PlanDev<T>& p, cx<T>* y, cx<T>* d) {
     using C = cx<T>;
     const int n = p.n_knots;
     if (!p.folded && threadIdx.x == 0) {   // unfolded plans (tiny knot sets): extension first, then a barrier
@@ -72,13 +73,25 @@ __device__ __forceinline__ void plan_apply_fn(const PlanDev<T>& p, cx<T>* y, cx<
         if (p.ext_lo && threadIdx.x == 0) y[0] = e_lo;
         if (p.ext_hi && threadIdx.x == 32 % blockDim.x) y[n - 1] = e_hi;
     }
-    __syncthreads();
+}
+
+// Stage 2 of plan_apply_fn: Hermite evaluation at the nq query carriers; emit(q, value).
+template <typename T, typename Emit>
+__device__ __forceinline__ void plan_hermite_stage(const PlanDev<T>& p, const cx<T>* y, const cx<T>* d, Emit emit) {
+    using C = cx<T>;
     for (int q = threadIdx.x; q < p.nq; q += blockDim.x) {
         int k = p.qk[q];
         T w0 = p.qw[q], w1 = p.qw[p.nq + q], w2 = p.qw[2 * p.nq + q], w3 = p.qw[3 * p.nq + q];   // four planes [4][nq]
         C y0 = y[k], y1 = y[k + 1], d0 = d[k], d1 = d[k + 1];
         emit(q, mk<T>(w0 * y0.x + w1 * d0.x + w2 * y1.x + w3 * d1.x, w0 * y0.y + w1 * d0.y + w2 * y1.y + w3 * d1.y));
     }
+}
+
+template <typename T, typename Emit>
+__device__ __forceinline__ void plan_apply_fn(const PlanDev<T>& p, cx<T>* y, cx<T>* d, Emit emit) {
+    plan_band_stage<T>(p, y, d);
+    __syncthreads();
+    plan_hermite_stage<T>(p, y, d, emit);
 }
 
 template <typename T>
