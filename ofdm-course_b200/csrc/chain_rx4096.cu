@@ -22,11 +22,6 @@
 const void* ofdm_upload_pilots(ofdm_ctx* ctx, const double* pv, size_t n_complex);
 uint32_t ofdm_reg_to_prev(const uint8_t* reg);
 
-__device__ __forceinline__ float2 ld_stream(const float2* p) {   // streaming load: do not allocate in L1
-    float2 r;
-    asm("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
 
 // Cache policy: the symbol stream goes through the copy engine and never touches L1, so what is left of L1 beside
 // 2 x 89 KB of shared memory (~55 KB) can hold the channel-estimate tables that every stream re-reads -- provided
@@ -71,10 +66,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// bulk L2 prefetch (no destination): keeps HBM -> L2 traffic running several symbols ahead of the loads
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Work item q of this CTA = (stream blockIdx.x + (q / S) * gridDim.x, symbol q % S).  Symbols are
@@ -84,7 +75,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   pass B  [256 k1 + 16 n2 + n3]    -> [258 k1 + 16 k2 + n3]                        (row pad of two samples)
 //   pass C  reads 16 consecutive n3 per (k1,k2) as eight 128-bit loads with immediate offsets: conflict-free
 //           because of the pad (129 k1 mod 8 is a permutation over a quarter warp).
-template <bool QAM16, bool NEAR, int LOADMODE>
+template <bool QAM16, bool NEAR>
 __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
@@ -153,40 +144,26 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         if (++pf_s == p.S) { pf_s = 0; pf_ptr += (int64_t)gridDim.x * stream_stride - (int64_t)(p.S - 1) * symlen; }
         else pf_ptr += symlen;
     };
-    const int PFD = 3;                            // LOADMODE 1: symbols prefetched into L2 ahead of the loads
     if (tid == 0) {
-        if (LOADMODE == 0) {
-            for (int i = 0; i < 2 && i < n_items; ++i) {
-                mbar_expect_tx(&bars[i], 32768u);
-                bulk_g2s(xb0 + i * XBUF, pf_ptr, 32768u, &bars[i]);
-                pf_advance();
-            }
-        } else {
-            for (int i = 0; i < PFD && i < n_items; ++i) { bulk_prefetch_l2(pf_ptr, 32768u); pf_advance(); }
+        for (int i = 0; i < 2 && i < n_items; ++i) {
+            mbar_expect_tx(&bars[i], 32768u);
+            bulk_g2s(xb0 + i * XBUF, pf_ptr, 32768u, &bars[i]);
+            pf_advance();
         }
     }
-    const float2* cur_ptr = rx0 + tid;            // LOADMODE 1: this thread's column of the current symbol
-    int cur_s = 0;
     int errs = 0, nears = 0;
     int s = 0, sf = 0, f = 0;
     int sfNd = 0;                                  // sf * Nd: row of the frame's decision buffer this symbol fills
     int64_t b = blockIdx.x;
     uint32_t parity = 0;
     for (int64_t q = 0; q < n_items; ++q) {
-        const int cur = LOADMODE == 0 ? (int)(q & 1) : 0;
+        const int cur = (int)(q & 1);
         float2* X = xb0 + cur * XBUF;
         float2 v[16];
-        if (LOADMODE == 0) {
-            mbar_wait(&bars[cur], parity);
-            parity ^= (uint32_t)cur;               // flips after both buffers have been used once
+        mbar_wait(&bars[cur], parity);
+        parity ^= (uint32_t)cur;                   // flips after both buffers have been used once
 #pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 16; ++n1) v[n1] = ld_stream(cur_ptr + 256 * n1);
-            if (++cur_s == p.S) { cur_s = 0; cur_ptr += (int64_t)gridDim.x * stream_stride - (int64_t)(p.S - 1) * symlen; }
-            else cur_ptr += symlen;
-        }
+        for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
         // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, in place
         fft16(v);
 #pragma unroll
@@ -230,15 +207,11 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             }
         }
         __syncthreads();                           // buffer `cur` is free: refill it with item q+2
-        if (tid == 0) {
-            if (LOADMODE == 0) {
-                if (q + 2 < n_items) {
-                    fence_proxy_async();
-                    mbar_expect_tx(&bars[cur], 32768u);
-                    bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
-                    pf_advance();
-                }
-            } else if (q + PFD < n_items) { bulk_prefetch_l2(pf_ptr, 32768u); pf_advance(); }
+        if (tid == 0 && q + 2 < n_items) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[cur], 32768u);
+            bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
+            pf_advance();
         }
         uint32_t txw[4] = {0u, 0u, 0u, 0u};
         if (sf == p.SpF - 1 && txbits) {           // reference words of this frame, consumed ~400 instructions later
@@ -386,15 +359,11 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     size_t smem = sizeof(float2) * (2 * XBUF + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 +
                   (size_t)lp->SpF * lp->Nd + sizeof(float2) * (size_t)lp->Np + 32;
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
-    if (const char* pad = getenv("OFDM_B200_SMEM_PAD")) smem += (size_t)atoi(pad);   // occupancy experiments only
     const bool q16 = lp->constellation == OFDM_16QAM;
     const bool near = near_eps > 0.0;
-    const int loadmode = getenv("OFDM_B200_LOADMODE") ? atoi(getenv("OFDM_B200_LOADMODE")) : 0;
     typedef void (*kern_t)(Fast4096Params, PlanDev<float>, DevConst<float>, const float2*, int64_t, const uint32_t*, uint32_t*, float2*, unsigned long long*,
                            int32_t*, float);
-    kern_t kern;
-    if (loadmode == 1) kern = q16 ? (near ? rx4096_kernel<true, true, 1> : rx4096_kernel<true, false, 1>) : (near ? rx4096_kernel<false, true, 1> : rx4096_kernel<false, false, 1>);
-    else kern = q16 ? (near ? rx4096_kernel<true, true, 0> : rx4096_kernel<true, false, 0>) : (near ? rx4096_kernel<false, true, 0> : rx4096_kernel<false, false, 0>);
+    kern_t kern = q16 ? (near ? rx4096_kernel<true, true> : rx4096_kernel<true, false>) : (near ? rx4096_kernel<false, true> : rx4096_kernel<false, false>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
     if (err_stream) CUDA_TRY(ctx, cudaMemsetAsync(err_stream, 0, sizeof(int32_t) * B, ctx->stream));
