@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     int slot4[4];
 #pragma unroll
     for (int m1 = 0; m1 < 4; ++m1) slot4[m1] = p.slot[tid + 256 * m1];
+    __shared__ float2 cs[16];                             // conjugated constellation (a divergent constant-bank index would serialise)
+    if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
     const float scale = 1.f / 4096.f;
     int par = 0;
     for (int f = 0; f < p.frames; ++f) {
@@ -195,9 +197,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
                 if (sl >= 0) {
                     const int q = sf * p.Nd + sl;
                     const uint32_t g = sm_get32(cur, q * p.bps, fw);
-                    int idx = 0;
-                    for (int i = 0; i < p.bps; ++i) idx = (idx << 1) | ((g >> i) & 1u);
-                    c = make_float2(p.con.re[idx], -p.con.im[idx]);
+                    c = cs[__brev(g) >> (32 - p.bps)];            // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
                 } else if (sl != SLOT_ZERO) { const float2 pv = p.pilots[(int64_t)s * p.Np + (-1 - sl)]; c = make_float2(pv.x, -pv.y); }
                 v[m1] = c;
             }
