@@ -186,76 +186,112 @@ extern "C" int ofdm_apply_fir(ofdm_ctx* ctx, const void* in, int64_t B, int64_t 
 // same order as add_noise_kernel followed by fir_kernel, without the 8 B/sample round trip in between.
 #define CH_TILE 2048
 #define CH_MAXD 1024
+#define CH_CHUNK 8         // tiles per CTA
+// Once per call: sigma of every stream (`Noise.m:3-5`: NoisePower = P / 10^(SNR/10), sigma = sqrt(NoisePower/2)) and
+// the ordered list of non-zero taps, so that the 250k tile CTAs of a sweep point start straight into the generator.
 template <typename T>
-__global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict__ in, int64_t L, const double* __restrict__ snr_db,
-                                                         const double* __restrict__ power_sum, const T* __restrict__ normals, uint64_t seed,
-                                                         int64_t first_stream, const cx<T>* __restrict__ h, int D, cx<T>* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cx<T>* sn = (cx<T>*)smem_raw;                   // CH_TILE + D - 1 noisy samples
-    cx<T>* hv = sn + CH_TILE + D - 1;               // non-zero taps, ascending delay
-    int* hd = (int*)(hv + D);
-    __shared__ T sigma_s;
-    __shared__ int nnz_s;
-    const int64_t b = blockIdx.x;
-    const int64_t n0 = (int64_t)blockIdx.y * CH_TILE;
-    if (threadIdx.x == 0) {
+__global__ void channel_prep_kernel(int64_t B, int64_t L, const double* __restrict__ snr_db, const double* __restrict__ power_sum,
+                                    const cx<T>* __restrict__ h, int D, T* __restrict__ sigma, cx<T>* __restrict__ hv, int* __restrict__ hd,
+                                    int* __restrict__ nnz) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) {
         const double P = power_sum[b] / (double)L;
-        sigma_s = (T)sqrt(P / pow(10.0, snr_db[b] / 10.0) / 2);
+        sigma[b] = (T)sqrt(P / pow(10.0, snr_db[b] / 10.0) / 2);
+    }
+    if (b == 0) {
         int k = 0;
         for (int d = 0; d < D; ++d) { const cx<T> t = h[d]; if (t.x != (T)0 || t.y != (T)0) { hv[k] = t; hd[k] = d; ++k; } }
-        nnz_s = k;
+        *nnz = k;
     }
-    __syncthreads();
-    const T sigma = sigma_s;
-    const int nnz = nnz_s;
-    const int64_t nlo = n0 - (D - 1);                // first staged sample (may be negative); sn[j] holds sample nlo + j
+}
+template <typename T>
+__global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict__ in, int64_t L, const T* __restrict__ sigma_g, const T* __restrict__ normals,
+                                                         uint64_t seed, int64_t first_stream, const cx<T>* __restrict__ hv, const int* __restrict__ hd,
+                                                         const int* __restrict__ nnz_g, int D, cx<T>* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<T>* sn = (cx<T>*)smem_raw;                   // D - 1 noisy samples of history, then the CH_TILE of the current tile
+    const int64_t b = blockIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.y * CH_CHUNK * CH_TILE;    // this CTA walks CH_CHUNK consecutive tiles, carrying the history
+    const T sigma = sigma_g[b];
+    const int nnz = *nnz_g;
+    const cx<T>* xin = in + b * L;
+    const T* nre = normals ? normals + (b * 2) * L : nullptr;
+    const T* nim = normals ? normals + (b * 2 + 1) * L : nullptr;
+    const uint64_t sid = (uint64_t)(first_stream + b);
+    // noisy sample n (0 outside the stream): x + sigma*(g1 + i g2), imported normals or the pair's Philox quad
+    auto noisy_imported = [&](int64_t n) -> cx<T> {
+        if (n < 0 || n >= L) return mk<T>(0, 0);
+        const cx<T> x = xin[n];
+        return mk<T>(x.x + sigma * nre[n], x.y + sigma * nim[n]);
+    };
+    auto noisy_pair = [&](int64_t pr, cx<T>& v0, cx<T>& v1) {          // samples 2 pr and 2 pr + 1 from one Philox call
+        v0 = mk<T>(0, 0); v1 = mk<T>(0, 0);
+        if (pr < 0 || 2 * pr >= L) return;
+        float g[4];
+        philox_normal_quad(seed, sid, (uint64_t)pr, g);
+        const cx<T> x0 = xin[2 * pr];
+        v0 = mk<T>(x0.x + sigma * (T)g[0], x0.y + sigma * (T)g[1]);
+        if (2 * pr + 1 < L) { const cx<T> x1 = xin[2 * pr + 1]; v1 = mk<T>(x1.x + sigma * (T)g[2], x1.y + sigma * (T)g[3]); }
+    };
+    // history of the first tile: samples c0 - (D-1) .. c0 - 1 (regenerated, not exchanged; c0 is even)
     if (normals) {
-        for (int j = threadIdx.x; j < CH_TILE + D - 1; j += 256) {
-            const int64_t n = nlo + j;
-            cx<T> v = mk<T>(0, 0);
-            if (n >= 0 && n < L) {
-                const cx<T> x = in[b * L + n];
-                v = mk<T>(x.x + sigma * normals[(b * 2) * L + n], x.y + sigma * normals[(b * 2 + 1) * L + n]);
-            }
-            sn[j] = v;
-        }
-    } else {                                         // sample pairs (2 pr, 2 pr + 1): one Philox call each
-        const int64_t pr0 = nlo >= 0 ? nlo >> 1 : -((-nlo + 1) >> 1);           // floor(nlo / 2)
-        const int npairs = (int)(((nlo + CH_TILE + D - 1 + 1) >> 1) - pr0) + 1;
-        for (int q = threadIdx.x; q < npairs; q += 256) {
-            const int64_t pr = pr0 + q;
-            float g[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pr >= 0 && 2 * pr < L) philox_normal_quad(seed, (uint64_t)(first_stream + b), (uint64_t)pr, g);
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int64_t n = 2 * pr + e;
-                const int64_t j = n - nlo;
-                if (j >= 0 && j < CH_TILE + D - 1) {
-                    cx<T> v = mk<T>(0, 0);
-                    if (n >= 0 && n < L) { const cx<T> x = in[b * L + n]; v = mk<T>(x.x + sigma * (T)g[2 * e], x.y + sigma * (T)g[2 * e + 1]); }
-                    sn[j] = v;
-                }
-            }
+        for (int j = threadIdx.x; j < D - 1; j += 256) sn[j] = noisy_imported(c0 - (D - 1) + j);
+    } else {
+        for (int q = threadIdx.x; 2 * q < D - 1; q += 256) {            // pair c0/2 - 1 - q covers samples c0 - 2q - 2, c0 - 2q - 1
+            cx<T> v0, v1;
+            noisy_pair((c0 >> 1) - 1 - q, v0, v1);
+            const int j1 = D - 2 - 2 * q;                               // slot of sample c0 - 2q - 1
+            sn[j1] = v1;
+            if (j1 >= 1) sn[j1 - 1] = v0;
         }
     }
-    __syncthreads();
-    // eight outputs per thread; the tap loop is outermost so that a tap is fetched once for all of them (the order of
-    // additions per output is still ascending delay)
-    cx<T> acc[CH_TILE / 256];
+    cx<T>* cur = sn + (D - 1);
+    for (int tile = 0; tile < CH_CHUNK; ++tile) {
+        const int64_t n0 = c0 + (int64_t)tile * CH_TILE;
+        if (n0 >= L) break;
+        if (normals) {
 #pragma unroll
-    for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = mk<T>(0, 0);
-    for (int t = 0; t < nnz; ++t) {
-        const int d = hd[t];
-        const cx<T> w = hv[t];
-        const cx<T>* sp = sn + threadIdx.x + D - 1 - d;
+            for (int i = 0; i < CH_TILE / 256; ++i) cur[threadIdx.x + 256 * i] = noisy_imported(n0 + threadIdx.x + 256 * i);
+        } else {
 #pragma unroll
-        for (int i = 0; i < CH_TILE / 256; ++i)
-            if ((int64_t)d <= n0 + threadIdx.x + 256 * i) acc[i] = acc[i] + cmul(sp[256 * i], w);
-    }
+            for (int i = 0; i < CH_TILE / 512; ++i) {
+                const int q = threadIdx.x + 256 * i;
+                cx<T> v0, v1;
+                noisy_pair((n0 >> 1) + q, v0, v1);
+                cur[2 * q] = v0; cur[2 * q + 1] = v1;
+            }
+        }
+        __syncthreads();
+        // eight outputs per thread; the tap loop is outermost so that a tap is fetched once for all of them (the order of
+        // additions per output is still ascending delay).  Samples before the start of the stream are absent, not zero.
+        cx<T> acc[CH_TILE / 256];
 #pragma unroll
-    for (int i = 0; i < CH_TILE / 256; ++i) {
-        const int64_t n = n0 + threadIdx.x + 256 * i;
-        if (n < L) out[b * L + n] = acc[i];
+        for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = mk<T>(0, 0);
+        if (n0 >= D) {
+            for (int t = 0; t < nnz; ++t) {
+                const cx<T> w = hv[t];
+                const cx<T>* sp = cur + threadIdx.x - hd[t];
+#pragma unroll
+                for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = acc[i] + cmul(sp[256 * i], w);
+            }
+        } else {
+            for (int t = 0; t < nnz; ++t) {
+                const int d = hd[t];
+                const cx<T> w = hv[t];
+                const cx<T>* sp = cur + threadIdx.x - d;
+#pragma unroll
+                for (int i = 0; i < CH_TILE / 256; ++i)
+                    if ((int64_t)d <= n0 + threadIdx.x + 256 * i) acc[i] = acc[i] + cmul(sp[256 * i], w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < CH_TILE / 256; ++i) {
+            const int64_t n = n0 + threadIdx.x + 256 * i;
+            if (n < L) out[b * L + n] = acc[i];
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < D - 1; j += 256) sn[j] = sn[CH_TILE + j];     // D - 1 <= CH_TILE: source and destination are disjoint
+        __syncthreads();
     }
 }
 
@@ -266,18 +302,26 @@ extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t
     if (B * L == 0) return OFDM_OK;
     size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
     if (snr_db && h && D >= 1 && D <= CH_MAXD && tx != rx) {
-        double* psum = (double*)ctx_scratch(ctx, sizeof(double) * B);
-        REQUIRE(ctx, psum != nullptr, "scratch allocation failed");
+        // scratch: power sums | sigma | compacted taps | their delays | tap count
+        const size_t o_sig = sizeof(double) * (size_t)B, o_hv = o_sig + sizeof(double) * (size_t)B, o_hd = o_hv + sizeof(double2) * (size_t)D,
+                     o_nnz = o_hd + sizeof(int) * (size_t)((D + 3) & ~3);
+        char* scr = (char*)ctx_scratch(ctx, o_nnz + 16);
+        REQUIRE(ctx, scr != nullptr, "scratch allocation failed");
+        double* psum = (double*)scr;
         CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
         const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
         DISPATCH_T(ctx, {
             stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)tx, L, psum);
             ctx->launches++;
-            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + 2 * D - 1) + sizeof(int) * (size_t)D;
+            channel_prep_kernel<T><<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(B, L, snr_db, psum, (const cx<T>*)h, D, (T*)(scr + o_sig), (cx<T>*)(scr + o_hv),
+                                                                                     (int*)(scr + o_hd), (int*)(scr + o_nnz));
+            ctx->launches++;
+            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + D - 1);
             auto k = channel_t5_kernel<T>;
             if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<dim3((unsigned)B, (unsigned)cdiv64(L, CH_TILE)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, snr_db, psum, (const T*)normals, seed, first_stream_id,
-                                                                                             (const cx<T>*)h, D, (cx<T>*)rx);
+            k<<<dim3((unsigned)B, (unsigned)cdiv64(L, (int64_t)CH_TILE * CH_CHUNK)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, (const T*)(scr + o_sig), (const T*)normals, seed,
+                                                                                             first_stream_id, (const cx<T>*)(scr + o_hv), (const int*)(scr + o_hd),
+                                                                                             (const int*)(scr + o_nnz), D, (cx<T>*)rx);
         });
         LAUNCH_CHECK(ctx);
         return OFDM_OK;
