@@ -241,11 +241,20 @@ typedef struct ofdm_link_params {
  * bits_dev: B streams x stream_bits (contiguous bitstream); time_dev: B x S x (Nfft+Tg).
  * (`Task 5/Main_model_Task_5.m:53-85`) */
 OFDM_API int ofdm_tx_chain(ofdm_ctx*, const ofdm_link_params*, const uint32_t* bits_dev, int64_t B, void* time_dev);
+/* Same, and also hands out sum |x|^2 of every stream (B doubles, cyclic prefixes included): the stream power `Noise.m:3`
+ * measures, accumulated while the samples are still in registers so that ofdm_channel_t5_p need not re-read the signal. */
+OFDM_API int ofdm_tx_chain_p(ofdm_ctx*, const ofdm_link_params*, const uint32_t* bits_dev, int64_t B, void* time_dev,
+                             double* power_sum_dev);
 /* Task-5 channel: AWGN (Philox or imported) then static multipath FIR
  * (`Task 5/Main_model_Task_5.m:108,123-127`); snr_db_dev may be NULL (no noise); h_dev NULL (no FIR). */
 OFDM_API int ofdm_channel_t5(ofdm_ctx*, const void* tx_dev, int64_t B, int64_t L, const double* snr_db_dev,
                              const void* normals_dev, uint64_t seed, int64_t first_stream_id,
                              const void* h_dev, int D, void* rx_dev);
+/* Same with the stream powers supplied (power_sum_dev: B doubles = sum |tx|^2 per stream, e.g. from ofdm_tx_chain_p);
+ * NULL makes it measure them itself, which is what ofdm_channel_t5 does (`Task 5/Noise.m:3-5`). */
+OFDM_API int ofdm_channel_t5_p(ofdm_ctx*, const void* tx_dev, int64_t B, int64_t L, const double* snr_db_dev,
+                               const double* power_sum_dev, const void* normals_dev, uint64_t seed, int64_t first_stream_id,
+                               const void* h_dev, int D, void* rx_dev);
 /* M1 RX chain: OFDM_demodulator -> LS_CE -> equalize_signal -> get_payload -> demapping ->
  * DeScrambler -> BER count, one pass over the stream (`Task 5/Task5_part2.m:169-174,269-303`).
  * rx_dev B x S x (Nfft+Tg); tx_bits_dev reference bits (B x stream_bits); outputs (each optional):

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, cons
 // symbol costs three block barriers.
 #define TXF_XROW 258
 #define TXF_XBUF 4128
-__global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out) {
+__global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out,
+                                                               double* __restrict__ power) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xb = (float2*)smem_raw;                       // two transform buffers
     const int fw = (p.frame_bits + 31) >> 5;
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
     const float scale = 1.f / 4096.f;
     int par = 0;
+    double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
     for (int f = 0; f < p.frames; ++f) {
         const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
         __syncthreads();                                   // previous frame's bit array is no longer read
@@ -247,6 +249,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
             fft16(v);
             float2* dst = out + (b * p.S + s) * (int64_t)(4096 + p.Tg);
             const int cp0 = 4096 - p.Tg;
+            float psym = 0.f;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -256,12 +259,24 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
                     const float2 y = make_float2(v[4 * c + d].x * scale, -v[4 * c + d].y * scale);
                     dst[p.Tg + n] = y;
                     if (n >= cp0) dst[n - cp0] = y;
+                    const float e = y.x * y.x + y.y * y.y;
+                    psym += n >= cp0 ? e + e : e;
                 }
+            pacc += (double)psym;
         }
+    }
+    if (power) {                                           // `Noise.m:3` needs mean |x|^2 of the stream: hand the sum to the channel stage
+        __shared__ double red[32];
+        const double tot = block_sum(pacc, red);
+        if (tid == 0) power[b] = tot;
     }
 }
 
+int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* power_sum);   // channel.cu
 extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time) {
+    return ofdm_tx_chain_p(ctx, lp, bits, B, time, nullptr);
+}
+extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, double* power) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, bits && time && B >= 0, "bad argument");
     if (B == 0) return OFDM_OK;
@@ -275,7 +290,7 @@ extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const ui
         const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * ((d.frame_bits + 31) / 32);
         if (ok && smem <= 110 * 1024) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(tx4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tx4096_kernel<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (float2*)time);
+            tx4096_kernel<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (float2*)time, power);
             LAUNCH_CHECK(ctx);
             return OFDM_OK;
         }
@@ -290,6 +305,7 @@ extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const ui
         k<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (cx<T>*)time);
     });
     LAUNCH_CHECK(ctx);
+    if (power) return ofdm_stream_power_sum(ctx, time, B, (int64_t)lp->S * (lp->Nfft + lp->Tg), power);   // generic shapes: separate pass
     return OFDM_OK;
 }
 

@@ -295,8 +295,22 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
     }
 }
 
+// sum |x|^2 per stream in double (first half of `Noise.m:3`); also used by ofdm_tx_chain_p for the shapes its fast kernel does not cover
+int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* psum) {
+    CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
+    if (B * L == 0) return OFDM_OK;
+    const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
+    DISPATCH_T(ctx, { stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, psum); });
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
 extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const void* normals,
                                uint64_t seed, int64_t first_stream_id, const void* h, int D, void* rx) {
+    return ofdm_channel_t5_p(ctx, tx, B, L, snr_db, nullptr, normals, seed, first_stream_id, h, D, rx);
+}
+extern "C" int ofdm_channel_t5_p(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const double* power_sum, const void* normals,
+                                 uint64_t seed, int64_t first_stream_id, const void* h, int D, void* rx) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, tx && rx && B >= 0 && L >= 0, "bad argument");
     if (B * L == 0) return OFDM_OK;
@@ -307,12 +321,13 @@ extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t
                      o_nnz = o_hd + sizeof(int) * (size_t)((D + 3) & ~3);
         char* scr = (char*)ctx_scratch(ctx, o_nnz + 16);
         REQUIRE(ctx, scr != nullptr, "scratch allocation failed");
-        double* psum = (double*)scr;
-        CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
-        const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
+        const double* psum = power_sum;
+        if (!psum) {                                  // no power handed over by the TX stage: one extra pass over the signal
+            int rc = ofdm_stream_power_sum(ctx, tx, B, L, (double*)scr);
+            if (rc) return rc;
+            psum = (const double*)scr;
+        }
         DISPATCH_T(ctx, {
-            stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)tx, L, psum);
-            ctx->launches++;
             channel_prep_kernel<T><<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(B, L, snr_db, psum, (const cx<T>*)h, D, (T*)(scr + o_sig), (cx<T>*)(scr + o_hv),
                                                                                      (int*)(scr + o_hd), (int*)(scr + o_nnz));
             ctx->launches++;

@@ -436,19 +436,25 @@ class Context:
         return xs[:k], cc[:k]
 
     # ---------------------------------------------------------------- fused chains
-    def tx_chain(self, lp, bits_dev, B):
+    def tx_chain(self, lp, bits_dev, B, want_power=False):
+        """TX chain; with ``want_power`` also returns sum |x|^2 per stream (float64, B) for ``channel_t5(power_sum=...)``."""
         out = self.empty_c(B, lp.S, lp.Nfft + lp.Tg)
-        self._chk(self.lib.ofdm_tx_chain(self.h, C.byref(lp), self.p(bits_dev), B, self.p(out)))
-        return out
+        if not want_power:
+            self._chk(self.lib.ofdm_tx_chain(self.h, C.byref(lp), self.p(bits_dev), B, self.p(out)))
+            return out
+        psum = torch.empty(B, dtype=torch.float64, device=self.device)
+        self._chk(self.lib.ofdm_tx_chain_p(self.h, C.byref(lp), self.p(bits_dev), B, self.p(out), self.p(psum)))
+        return out, psum
 
-    def channel_t5(self, tx_dev, snr_db=None, h_dev=None, normals_dev=None, seed=0, first_stream_id=0, out=None):
+    def channel_t5(self, tx_dev, snr_db=None, h_dev=None, normals_dev=None, seed=0, first_stream_id=0, out=None, power_sum=None):
         x = tx_dev.reshape(tx_dev.shape[0], -1)
         B, L = x.shape
         s = self.real(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (B,)).copy()) if snr_db is not None else None
         if out is None:
             out = torch.empty_like(x)
         D = h_dev.shape[-1] if h_dev is not None else 0
-        self._chk(self.lib.ofdm_channel_t5(self.h, self.p(x), B, L, self.p(s), self.p(normals_dev), seed, first_stream_id, self.p(h_dev), D, self.p(out)))
+        self._chk(self.lib.ofdm_channel_t5_p(self.h, self.p(x), B, L, self.p(s), self.p(power_sum), self.p(normals_dev), seed, first_stream_id, self.p(h_dev), D,
+                                             self.p(out)))
         return out.reshape(tx_dev.shape)
 
     def rx_chain_t5(self, lp, rx_dev, B, tx_bits_dev=None, want_bits=True, want_H=True, counts=None, near_eps=0.0, want_err_per_stream=False,

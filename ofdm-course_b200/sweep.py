@@ -60,8 +60,8 @@ def ber_sweep_task5(ctx, lp, snrs_db, streams_per_point, block, taps_h, seed=1, 
         gen = torch.Generator(device=ctx.device)
         gen.manual_seed(seed * 1_000_003 + gid0)
         bits = torch.randint(-2**31, 2**31 - 1, (n * words,), dtype=torch.int32, device=ctx.device, generator=gen)
-        tx = ctx.tx_chain(lp, bits, n)
-        rx = ctx.channel_t5(tx, snr_db=float(snr_db), h_dev=h_dev, seed=seed, first_stream_id=gid0)
+        tx, psum = ctx.tx_chain(lp, bits, n, want_power=True)       # stream power measured in the TX kernel's registers
+        rx = ctx.channel_t5(tx, snr_db=float(snr_db), h_dev=h_dev, seed=seed, first_stream_id=gid0, power_sum=psum)
         res = ctx.rx_chain_t5(lp, rx, n, tx_bits_dev=bits, want_bits=False, want_H=False, near_eps=near_eps)
         return res["counts"].cpu().numpy()
 

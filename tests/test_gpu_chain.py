@@ -132,6 +132,36 @@ def test_channel_t5_device_matches_oracle_and_philox_is_batch_invariant(G):
     assert np.array_equal(full[1], second[0])
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_tx_power_handover_and_fused_channel_equals_two_step_channel(G, prec):
+    """ofdm_tx_chain_p / ofdm_channel_t5_p: the TX stage measures sum |x|^2 (`Noise.m:3`) so the channel stage skips
+    its own pass; and the fused Philox channel (tiles with carried history) equals add_noise -> apply_fir exactly."""
+    import torch
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context(prec)
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(11)
+    B = 3
+    bits = ctx.bits(rng.integers(0, 2, B * p.stream_bits).astype(np.uint8))
+    tx0 = ctx.tx_chain(lp, bits, B)
+    tx, psum = ctx.tx_chain(lp, bits, B, want_power=True)
+    assert torch.equal(torch.view_as_real(tx), torch.view_as_real(tx0))
+    t64 = tx.reshape(B, -1).to(torch.complex128)
+    ref = (t64.real ** 2 + t64.imag ** 2).sum(dim=1)
+    assert float(((psum - ref).abs() / ref).max()) < (1e-6 if prec == "f32" else 1e-12)
+    hd = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
+    own = ctx.channel_t5(tx, snr_db=12.0, h_dev=hd, seed=9, first_stream_id=5)
+    handed = ctx.channel_t5(tx, snr_db=12.0, h_dev=hd, seed=9, first_stream_id=5, power_sum=psum)
+    assert rel_err(handed.cpu().numpy(), own.cpu().numpy()) < (1e-6 if prec == "f32" else 1e-12)
+    # two-step composition through the reference-named functions: Noise then conv+truncate (`Main_model_Task_5.m:108,123-127`)
+    noisy = ctx.channel_t5(tx, snr_db=12.0, seed=9, first_stream_id=5)
+    two_step = ctx.channel_t5(noisy, h_dev=hd)
+    if prec == "f32":
+        assert torch.equal(torch.view_as_real(own), torch.view_as_real(two_step))
+    else:   # the FP64 kernels contract their multiply-adds differently
+        assert rel_err(own.cpu().numpy(), two_step.cpu().numpy()) < 1e-14
+
+
 def test_rx_chain_host_entry(G):
     import torch
     p = OC.params_task5(comb=4)

@@ -14,8 +14,8 @@ for rep in range(3):
     print("rep", rep)
     gen = torch.Generator(device=ctx.device); gen.manual_seed(5 + rep)
     bits = T("randint", lambda: torch.randint(-2**31, 2**31 - 1, (n * words,), dtype=torch.int32, device=ctx.device, generator=gen))
-    tx = T("tx_chain", lambda: ctx.tx_chain(lp, bits, n))
-    rx = T("channel_t5", lambda: ctx.channel_t5(tx, snr_db=10.0, h_dev=h_dev, seed=1, first_stream_id=rep * n))
+    tx, ps = T("tx_chain", lambda: ctx.tx_chain(lp, bits, n, want_power=True))
+    rx = T("channel_t5", lambda: ctx.channel_t5(tx, snr_db=10.0, h_dev=h_dev, seed=1, first_stream_id=rep * n, power_sum=ps))
     res = T("rx_chain_t5", lambda: ctx.rx_chain_t5(lp, rx, n, tx_bits_dev=bits, want_bits=False, want_H=False))
     T("counts.cpu", lambda: res["counts"].cpu().numpy())
     del tx, rx
