@@ -160,7 +160,7 @@ __global__ void fir_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, c
         cx<T> acc = mk<T>(0, 0);
         for (int t = 0; t < nnz; ++t) {
             const int d = hd[t];
-            if ((int64_t)d <= n) acc = acc + cmul(x[n - d], hv[t]);
+            if ((int64_t)d <= n) acc = cmac(acc, x[n - d], hv[t]);
         }
         out[b * L + n] = acc;
     }
@@ -206,14 +206,17 @@ __global__ void channel_prep_kernel(int64_t B, int64_t L, const double* __restri
 }
 template <typename T>
 __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict__ in, int64_t L, const T* __restrict__ sigma_g, const T* __restrict__ normals,
-                                                         uint64_t seed, int64_t first_stream, const cx<T>* __restrict__ hv, const int* __restrict__ hd,
+                                                         uint64_t seed, int64_t first_stream, const cx<T>* __restrict__ hv_g, const int* __restrict__ hd_g,
                                                          const int* __restrict__ nnz_g, int D, cx<T>* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sn = (cx<T>*)smem_raw;                   // D - 1 noisy samples of history, then the CH_TILE of the current tile
+    cx<T>* hv = sn + CH_TILE + D - 1;               // non-zero taps, ascending delay
+    int* hd = (int*)(hv + D);
     const int64_t b = blockIdx.x;
     const int64_t c0 = (int64_t)blockIdx.y * CH_CHUNK * CH_TILE;    // this CTA walks CH_CHUNK consecutive tiles, carrying the history
     const T sigma = sigma_g[b];
     const int nnz = *nnz_g;
+    for (int t = threadIdx.x; t < nnz; t += 256) { hv[t] = hv_g[t]; hd[t] = hd_g[t]; }
     const cx<T>* xin = in + b * L;
     const T* nre = normals ? normals + (b * 2) * L : nullptr;
     const T* nim = normals ? normals + (b * 2 + 1) * L : nullptr;
@@ -249,9 +252,22 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
     for (int tile = 0; tile < CH_CHUNK; ++tile) {
         const int64_t n0 = c0 + (int64_t)tile * CH_TILE;
         if (n0 >= L) break;
+        const bool whole = n0 + CH_TILE <= L;               // no range test inside a whole tile
         if (normals) {
 #pragma unroll
             for (int i = 0; i < CH_TILE / 256; ++i) cur[threadIdx.x + 256 * i] = noisy_imported(n0 + threadIdx.x + 256 * i);
+        } else if (whole) {
+            const cx<T>* xp = xin + n0;
+            const uint64_t pr0 = (uint64_t)(n0 >> 1);
+#pragma unroll
+            for (int i = 0; i < CH_TILE / 512; ++i) {
+                const int q = threadIdx.x + 256 * i;
+                float g[4];
+                philox_normal_quad(seed, sid, pr0 + (uint64_t)q, g);
+                const cx<T> x0 = xp[2 * q], x1 = xp[2 * q + 1];
+                cur[2 * q] = mk<T>(x0.x + sigma * (T)g[0], x0.y + sigma * (T)g[1]);
+                cur[2 * q + 1] = mk<T>(x1.x + sigma * (T)g[2], x1.y + sigma * (T)g[3]);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < CH_TILE / 512; ++i) {
@@ -272,7 +288,7 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
                 const cx<T> w = hv[t];
                 const cx<T>* sp = cur + threadIdx.x - hd[t];
 #pragma unroll
-                for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = acc[i] + cmul(sp[256 * i], w);
+                for (int i = 0; i < CH_TILE / 256; ++i) acc[i] = cmac(acc[i], sp[256 * i], w);
             }
         } else {
             for (int t = 0; t < nnz; ++t) {
@@ -281,13 +297,17 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
                 const cx<T>* sp = cur + threadIdx.x - d;
 #pragma unroll
                 for (int i = 0; i < CH_TILE / 256; ++i)
-                    if ((int64_t)d <= n0 + threadIdx.x + 256 * i) acc[i] = acc[i] + cmul(sp[256 * i], w);
+                    if ((int64_t)d <= n0 + threadIdx.x + 256 * i) acc[i] = cmac(acc[i], sp[256 * i], w);
             }
         }
+        cx<T>* op = out + b * L + n0 + threadIdx.x;
+        if (whole) {
 #pragma unroll
-        for (int i = 0; i < CH_TILE / 256; ++i) {
-            const int64_t n = n0 + threadIdx.x + 256 * i;
-            if (n < L) out[b * L + n] = acc[i];
+            for (int i = 0; i < CH_TILE / 256; ++i) op[256 * i] = acc[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < CH_TILE / 256; ++i)
+                if (n0 + threadIdx.x + 256 * i < L) op[256 * i] = acc[i];
         }
         __syncthreads();
         for (int j = threadIdx.x; j < D - 1; j += 256) sn[j] = sn[CH_TILE + j];     // D - 1 <= CH_TILE: source and destination are disjoint
@@ -331,7 +351,7 @@ extern "C" int ofdm_channel_t5_p(ofdm_ctx* ctx, const void* tx, int64_t B, int64
             channel_prep_kernel<T><<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(B, L, snr_db, psum, (const cx<T>*)h, D, (T*)(scr + o_sig), (cx<T>*)(scr + o_hv),
                                                                                      (int*)(scr + o_hd), (int*)(scr + o_nnz));
             ctx->launches++;
-            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + D - 1);
+            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + 2 * D - 1) + sizeof(int) * (size_t)D;
             auto k = channel_t5_kernel<T>;
             if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k<<<dim3((unsigned)B, (unsigned)cdiv64(L, (int64_t)CH_TILE * CH_CHUNK)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, (const T*)(scr + o_sig), (const T*)normals, seed,

@@ -24,6 +24,15 @@ __host__ __device__ __forceinline__ double2 operator+(double2 a, double2 b) { re
 __host__ __device__ __forceinline__ double2 operator-(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __host__ __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// acc + x*w as four fused multiply-adds, the SAMPLE as the broadcast operand: on sm_100 two FFMA2 (a scalar broadcast is a free
+// operand modifier of the packed pipe, a half swap is not -- tools/ubench_fp32x2_mod.cu), with (-w.y, w.x) hoisted per tap
+__device__ __forceinline__ float2 cmac(float2 acc, float2 x, float2 w) {
+    acc = __ffma2_rn(make_float2(x.x, x.x), w, acc);
+    return __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), acc);
+}
+__device__ __forceinline__ double2 cmac(double2 acc, double2 x, double2 w) {
+    return make_double2(fma(x.y, -w.y, fma(x.x, w.x, acc.x)), fma(x.y, w.x, fma(x.x, w.y, acc.y)));
+}
 // a * conj(b)
 __host__ __device__ __forceinline__ float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
 __host__ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
