@@ -17,16 +17,18 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
 }
 // Unit normals for a PAIR of samples (2*pair, 2*pair + 1) of a stream from ONE Philox call: the four 32-bit outputs
 // feed two Box-Muller transforms, (g[0], g[1]) = real/imaginary normal of the even sample, (g[2], g[3]) of the odd one.
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ void philox_normal_quad(uint64_t seed, uint64_t stream, uint64_t pair, float g[4]) {
     uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;   // (0,1]
-        const float u2 = (float)c[2 * h + 1] * 2.3283064365386963e-10f;        // [0,1)
-        const float r = sqrtf(-2.0f * __logf(u1));
+        // u1 = (c+1) 2^-32 in (0,1] is never denormal, so the bare MUFU forms do: r = sqrt(-2 ln u1) = sqrt(-2 ln2 * log2 u1)
+        const float u1 = ((float)c[2 * h] + 1.0f) * 2.3283064365386963e-10f;
+        const float r = sqrt_approx(lg2_approx(u1) * -1.3862943611198906f);
         float s, co;
-        __sincosf(6.283185307179586f * u2, &s, &co);
+        __sincosf((float)c[2 * h + 1] * 1.4629180792671596e-9f, &s, &co);     // 2 pi u2, u2 = c 2^-32 in [0,1)
         g[2 * h] = r * co; g[2 * h + 1] = r * s;
     }
 }

@@ -156,6 +156,8 @@ def test_sto_cfo_noise_channel(G):
     e = noisy - clean
     assert abs(np.mean(np.abs(e) ** 2) - 0.1) < 2e-3 and abs(np.mean(e)) < 3e-3 and abs(nv - np.sqrt(0.1)) < 1e-6
     assert abs(np.mean(e.real * e.imag)) < 1e-3
+    g = np.concatenate([e.real, e.imag]) / np.sqrt(0.05)      # unit normals: fourth moment 3, P(|g| > 3) = 0.0027 (Box-Muller on the bare MUFU forms)
+    assert abs(np.mean(g ** 4) - 3) < 0.08 and abs(np.mean(np.abs(g) > 3) - 0.0027) < 5e-4
     h_ref, H_ref = O.get_MP_channel_resp(TAPS5, 4096)
     h, H = G.get_MP_channel_resp(TAPS5, 4096, precision="f64")
     assert np.array_equal(h, h_ref) and rel_err(H, H_ref) < 1e-13
