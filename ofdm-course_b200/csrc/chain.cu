@@ -163,6 +163,14 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     int slot4[4];
 #pragma unroll
     for (int m1 = 0; m1 < 4; ++m1) slot4[m1] = p.slot[tid + 256 * m1];
+    int pidx[4];                                          // pilot column row of a pilot carrier (0 otherwise: loaded, not used)
+    float2 pv[4];
+#pragma unroll
+    for (int m1 = 0; m1 < 4; ++m1) {
+        pidx[m1] = (slot4[m1] < 0 && slot4[m1] != SLOT_ZERO) ? -1 - slot4[m1] : 0;
+        pv[m1] = p.pilots[pidx[m1]];                      // symbol 0
+    }
+    const bool aligned = (32 % p.bps) == 0;
     __shared__ float2 cs[16];                             // conjugated constellation (a divergent constant-bank index would serialise)
     if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
     const float scale = 1.f / 4096.f;
@@ -180,8 +188,13 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
         uint32_t* cur = s0; uint32_t* nxt = s1;
         if (p.scramble) {
             for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
-                for (int w = tid; w < fw; w += CH_THREADS)
-                    nxt[w] = cur[w] ^ sm_get32(cur, 32 * w - sh13, fw) ^ sm_get32(cur, 32 * w - sh14, fw);
+                if (((sh13 | sh14) & 31) == 0) {           // from the sixth doubling on both shifts are whole words
+                    const int d13 = sh13 >> 5, d14 = sh14 >> 5;
+                    for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ (w >= d13 ? cur[w - d13] : 0u) ^ (w >= d14 ? cur[w - d14] : 0u);
+                } else {
+                    for (int w = tid; w < fw; w += CH_THREADS)
+                        nxt[w] = cur[w] ^ sm_get32(cur, 32 * w - sh13, fw) ^ sm_get32(cur, 32 * w - sh14, fw);
+                }
                 __syncthreads();
                 uint32_t* t = cur; cur = nxt; nxt = t;
             }
@@ -191,17 +204,19 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
             float2* X = xb + par * TXF_XBUF;
             par ^= 1;
             float2 v[16];
-            // ---- carriers of this thread, conjugated (mapping.m:14-21, OFDM_map_carriers.m:3-7)
+            // ---- carriers of this thread, conjugated (mapping.m:14-21, OFDM_map_carriers.m:3-7).  Every lane runs the data path
+            // on a clamped slot and picks afterwards: a comb layout mixes data and pilot lanes in every warp.
 #pragma unroll
             for (int m1 = 0; m1 < 4; ++m1) {
                 const int sl = slot4[m1];
-                float2 c = make_float2(0.f, 0.f);
-                if (sl >= 0) {
-                    const int q = sf * p.Nd + sl;
-                    const uint32_t g = sm_get32(cur, q * p.bps, fw);
-                    c = cs[__brev(g) >> (32 - p.bps)];            // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
-                } else if (sl != SLOT_ZERO) { const float2 pv = p.pilots[(int64_t)s * p.Np + (-1 - sl)]; c = make_float2(pv.x, -pv.y); }
-                v[m1] = c;
+                const int qb = (sf * p.Nd + max(sl, 0)) * p.bps;
+                const uint32_t g = aligned ? cur[qb >> 5] >> (qb & 31) : sm_get32(cur, qb, fw);   // bps | 32: a group never straddles a word
+                const float2 cd = cs[__brev(g) >> (32 - p.bps)];      // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
+                v[m1] = sl >= 0 ? cd : (sl != SLOT_ZERO ? make_float2(pv[m1].x, -pv[m1].y) : make_float2(0.f, 0.f));
+            }
+            if (s + 1 < p.S) {                                        // next symbol's pilot column, in flight during the transform
+#pragma unroll
+                for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)(s + 1) * p.Np + pidx[m1]];
             }
 #pragma unroll
             for (int m1 = 4; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
