@@ -143,13 +143,12 @@ __global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, cons
 #define TXF_XROW 258
 #define TXF_XBUF 4128
 __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out,
-                                                               double* __restrict__ power) {
+                                                               double* __restrict__ power, int64_t B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xb = (float2*)smem_raw;                       // two transform buffers
     const int fw = (p.frame_bits + 31) >> 5;
     uint32_t* s0 = (uint32_t*)(xb + 2 * TXF_XBUF);
     uint32_t* s1 = s0 + fw;
-    const int64_t b = blockIdx.x;
     const int tid = threadIdx.x;
     const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
     float2 ta[16], tb[16];
@@ -175,6 +174,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
     const float scale = 1.f / 4096.f;
     int par = 0;
+    // persistent CTA: the per-thread twiddles, slot roles and the constellation table are set up once for all its streams
+    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
     for (int f = 0; f < p.frames; ++f) {
         const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
@@ -214,9 +215,10 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
                 const float2 cd = cs[__brev(g) >> (32 - p.bps)];      // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
                 v[m1] = sl >= 0 ? cd : (sl != SLOT_ZERO ? make_float2(pv[m1].x, -pv[m1].y) : make_float2(0.f, 0.f));
             }
-            if (s + 1 < p.S) {                                        // next symbol's pilot column, in flight during the transform
+            {                                                         // next symbol's pilot column (the next stream's first), in flight during the transform
+                const int sn = s + 1 < p.S ? s + 1 : 0;
 #pragma unroll
-                for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)(s + 1) * p.Np + pidx[m1]];
+                for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)sn * p.Np + pidx[m1]];
             }
 #pragma unroll
             for (int m1 = 4; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
@@ -285,6 +287,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
         const double tot = block_sum(pacc, red);
         if (tid == 0) power[b] = tot;
     }
+    }
 }
 
 int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* power_sum);   // channel.cu
@@ -305,7 +308,8 @@ extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const 
         const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * ((d.frame_bits + 31) / 32);
         if (ok && smem <= 110 * 1024) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(tx4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tx4096_kernel<<<(unsigned)B, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (float2*)time, power);
+            tx4096_kernel<<<(unsigned)std::min<int64_t>(B, 2 * (int64_t)ctx->sm_count), CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames,
+                                                                                                                   (float2*)time, power, B);
             LAUNCH_CHECK(ctx);
             return OFDM_OK;
         }
