@@ -175,26 +175,45 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     const float scale = 1.f / 4096.f;
     int par = 0;
     // persistent CTA: the per-thread twiddles, slot roles and the constellation table are set up once for all its streams
+    // the payload words of the next frame are requested while the current one is transformed (three per thread cover 24,576-bit frames)
+    uint32_t nb[3] = {0u, 0u, 0u};
+    auto fetch_frame = [&](int64_t bb, int ff) {
+        const int64_t base = bb * stream_bits + (int64_t)ff * p.frame_bits;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int w = tid + CH_THREADS * j;
+            if (w < fw) nb[j] = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+        }
+    };
+    if ((int64_t)blockIdx.x < B) fetch_frame(blockIdx.x, 0);
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
     for (int f = 0; f < p.frames; ++f) {
         const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
         __syncthreads();                                   // previous frame's bit array is no longer read
-        for (int w = tid; w < fw; w += CH_THREADS) {
-            uint32_t v = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
-            if (w == 0 && p.scramble) v ^= (p.prev0 >> 19) ^ (p.prev0 >> 18);   // fold the register pre-history into the input
-            s0[w] = v;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int w = tid + CH_THREADS * j;
+            if (w < fw) s0[w] = (w == 0 && p.scramble) ? nb[j] ^ (p.prev0 >> 19) ^ (p.prev0 >> 18) : nb[j];   // fold the register pre-history into the input
         }
+        for (int w = tid + 3 * CH_THREADS; w < fw; w += CH_THREADS) s0[w] = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
         __syncthreads();
+        if (f + 1 < p.frames) fetch_frame(b, f + 1);
+        else if (b + gridDim.x < B) fetch_frame(b + gridDim.x, 0);
         uint32_t* cur = s0; uint32_t* nxt = s1;
         if (p.scramble) {
             for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
                 if (((sh13 | sh14) & 31) == 0) {           // from the sixth doubling on both shifts are whole words
                     const int d13 = sh13 >> 5, d14 = sh14 >> 5;
                     for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ (w >= d13 ? cur[w - d13] : 0u) ^ (w >= d14 ? cur[w - d14] : 0u);
-                } else {
-                    for (int w = tid; w < fw; w += CH_THREADS)
-                        nxt[w] = cur[w] ^ sm_get32(cur, 32 * w - sh13, fw) ^ sm_get32(cur, 32 * w - sh14, fw);
+                } else {                                   // bits [32w - sh, 32w - sh + 32) straddle words w - q - 1 and w - q (sh = 32 q + r); words before the frame are zero
+                    const int q13 = sh13 >> 5, r13 = sh13 & 31, q14 = sh14 >> 5, r14 = sh14 & 31;
+                    for (int w = tid; w < fw; w += CH_THREADS) {
+                        const int i13 = w - q13, i14 = w - q14;
+                        const uint32_t a = __funnelshift_l(i13 >= 1 ? cur[i13 - 1] : 0u, i13 >= 0 ? cur[i13] : 0u, r13);
+                        const uint32_t c = __funnelshift_l(i14 >= 1 ? cur[i14 - 1] : 0u, i14 >= 0 ? cur[i14] : 0u, r14);
+                        nxt[w] = cur[w] ^ a ^ c;
+                    }
                 }
                 __syncthreads();
                 uint32_t* t = cur; cur = nxt; nxt = t;
