@@ -142,13 +142,18 @@ __global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, cons
 // symbol costs three block barriers.
 #define TXF_XROW 258
 #define TXF_XBUF 4128
+#define TXF_PAD(fw) ((fw) + ((fw) >> 3) + 2)
 __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out,
                                                                double* __restrict__ power, int64_t B) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xb = (float2*)smem_raw;                       // two transform buffers
     const int fw = (p.frame_bits + 31) >> 5;
-    uint32_t* s0 = (uint32_t*)(xb + 2 * TXF_XBUF);
-    uint32_t* s1 = s0 + fw;
+    // two frame bit arrays, each preceded by fw zero words: the scrambler's shifted reads need no range test
+    // (pad = fw + fw/8 + 2 words: the x^14 shift of the last doubling reaches 14/13 of a frame back)
+    const int pad = TXF_PAD(fw);
+    uint32_t* s0 = (uint32_t*)(xb + 2 * TXF_XBUF) + pad;
+    uint32_t* s1 = s0 + fw + pad;
+    for (int w = threadIdx.x; w < pad; w += CH_THREADS) { s0[w - pad] = 0u; s1[w - pad] = 0u; }
     const int tid = threadIdx.x;
     const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
     float2 ta[16], tb[16];
@@ -205,13 +210,13 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
             for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
                 if (((sh13 | sh14) & 31) == 0) {           // from the sixth doubling on both shifts are whole words
                     const int d13 = sh13 >> 5, d14 = sh14 >> 5;
-                    for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ (w >= d13 ? cur[w - d13] : 0u) ^ (w >= d14 ? cur[w - d14] : 0u);
-                } else {                                   // bits [32w - sh, 32w - sh + 32) straddle words w - q - 1 and w - q (sh = 32 q + r); words before the frame are zero
+                    for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ cur[w - d13] ^ cur[w - d14];
+                } else {                                   // bits [32w - sh, 32w - sh + 32) straddle words w - q - 1 and w - q (sh = 32 q + r); the words before the frame are the zero pad
                     const int q13 = sh13 >> 5, r13 = sh13 & 31, q14 = sh14 >> 5, r14 = sh14 & 31;
                     for (int w = tid; w < fw; w += CH_THREADS) {
                         const int i13 = w - q13, i14 = w - q14;
-                        const uint32_t a = __funnelshift_l(i13 >= 1 ? cur[i13 - 1] : 0u, i13 >= 0 ? cur[i13] : 0u, r13);
-                        const uint32_t c = __funnelshift_l(i14 >= 1 ? cur[i14 - 1] : 0u, i14 >= 0 ? cur[i14] : 0u, r14);
+                        const uint32_t a = __funnelshift_l(cur[i13 - 1], cur[i13], r13);
+                        const uint32_t c = __funnelshift_l(cur[i14 - 1], cur[i14], r14);
                         nxt[w] = cur[w] ^ a ^ c;
                     }
                 }
@@ -324,7 +329,8 @@ extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const 
         bool ok = true;                                   // every occupied row must lie in 1..1024
         for (int i = 0; i < lp->Nd && ok; ++i) ok = lp->data_carriers_host[i] <= 1024;
         for (int i = 0; i < lp->Np && ok; ++i) ok = lp->pilot_carriers_host[i] <= 1024;
-        const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * ((d.frame_bits + 31) / 32);
+        const int fw = (d.frame_bits + 31) / 32;
+        const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * (size_t)(fw + TXF_PAD(fw));   // two bit arrays + their zero pads
         if (ok && smem <= 110 * 1024) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(tx4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             tx4096_kernel<<<(unsigned)std::min<int64_t>(B, 2 * (int64_t)ctx->sm_count), CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames,
