@@ -162,7 +162,10 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     {
         const int m3 = tid & 15;
 #pragma unroll
-        for (int q2 = 0; q2 < 16; ++q2) tb[q2] = p.tw[(16 * m3 * q2) & 4095];         // W256^{m3*q2}
+        for (int q2 = 0; q2 < 16; ++q2) {                                             // W256^{m3*q2} / 4096: ifft's 1/N is a power of two,
+            const float2 w = p.tw[(16 * m3 * q2) & 4095];                             // so folding it into the twiddle is exact
+            tb[q2] = make_float2(w.x * (1.f / 4096.f), w.y * (1.f / 4096.f));
+        }
     }
     int slot4[4];
 #pragma unroll
@@ -177,7 +180,6 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     const bool aligned = (32 % p.bps) == 0;
     __shared__ float2 cs[16];                             // conjugated constellation (a divergent constant-bank index would serialise)
     if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
-    const float scale = 1.f / 4096.f;
     int par = 0;
     // persistent CTA: the per-thread twiddles, slot roles and the constellation table are set up once for all its streams
     // the payload words of the next frame are requested while the current one is transformed (three per thread cover 24,576-bit frames)
@@ -244,10 +246,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
 #pragma unroll
                 for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)sn * p.Np + pidx[m1]];
             }
-#pragma unroll
-            for (int m1 = 4; m1 < 16; ++m1) v[m1] = make_float2(0.f, 0.f);
-            // ---- pass A
-            fft16(v);
+            // ---- pass A (rows 4..15 of the column are empty)
+            fft16_in4(v);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
                     for (int d = 0; d < 4; ++d) {
                         const int q2 = c + 4 * d;
                         float2 x = v[4 * c + d];
-                        if (q2) x = cmul(x, tb[q2]);
+                        x = q2 ? cmul(x, tb[q2]) : make_float2(x.x * tb[0].x, x.y * tb[0].x);
                         wp[16 * q2] = x;
                     }
             }
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
                 for (int d = 0; d < 4; ++d) {
                     const int q3 = c + 4 * d;
                     const int n = tid + 256 * q3;
-                    const float2 y = make_float2(v[4 * c + d].x * scale, -v[4 * c + d].y * scale);
+                    const float2 y = make_float2(v[4 * c + d].x, -v[4 * c + d].y);
                     dst[p.Tg + n] = y;
                     if (n >= cp0) dst[n - cp0] = y;
                     const float e = y.x * y.x + y.y * y.y;

@@ -38,6 +38,23 @@ __device__ __forceinline__ void fft16_steps12(float2* v) {
     t = v[14]; v[14] = make_float2((t.y - t.x) * RSQ2, -(t.x + t.y) * RSQ2);                      // W16^6
     t = v[15]; v[15] = make_float2(-t.x * C16_1 - t.y * S16_1, t.x * S16_1 - t.y * C16_1);      // W16^9
 }
+// Same transform when only v[0..3] are non-zero (the TX side: rows 1..1024 of 4096 carry carriers): the first radix-4
+// stage degenerates to copies, so it is the twiddles and the second stage only.
+__device__ __forceinline__ void fft16_in4(float2* v) {
+    const float2 x1 = v[1], x2 = v[2], x3 = v[3];
+    v[4] = v[0]; v[8] = v[0]; v[12] = v[0];
+    v[5]  = make_float2(x1.x * C16_1 + x1.y * S16_1, x1.y * C16_1 - x1.x * S16_1);            // W16^1
+    v[6]  = make_float2((x2.x + x2.y) * RSQ2, (x2.y - x2.x) * RSQ2);                            // W16^2
+    v[7]  = make_float2(x3.x * S16_1 + x3.y * C16_1, x3.y * S16_1 - x3.x * C16_1);            // W16^3
+    v[9]  = make_float2((x1.x + x1.y) * RSQ2, (x1.y - x1.x) * RSQ2);                            // W16^2
+    v[10] = make_float2(x2.y, -x2.x);                                                            // W16^4 = -i
+    v[11] = make_float2((x3.y - x3.x) * RSQ2, -(x3.x + x3.y) * RSQ2);                           // W16^6
+    v[13] = make_float2(x1.x * S16_1 + x1.y * C16_1, x1.y * S16_1 - x1.x * C16_1);            // W16^3
+    v[14] = make_float2((x2.y - x2.x) * RSQ2, -(x2.x + x2.y) * RSQ2);                           // W16^6
+    v[15] = make_float2(-x3.x * C16_1 - x3.y * S16_1, x3.x * S16_1 - x3.y * C16_1);           // W16^9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) fft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
 __device__ __forceinline__ void fft16(float2* v) {
     fft16_steps12(v);
 #pragma unroll
