@@ -162,6 +162,29 @@ def test_tx_power_handover_and_fused_channel_equals_two_step_channel(G, prec):
         assert rel_err(own.cpu().numpy(), two_step.cpu().numpy()) < 1e-14
 
 
+@pytest.mark.parametrize("L,D", [(5001, 7), (100, 1), (2048, 26), (4097, 2), (20001, 300)])
+def test_fused_channel_on_ragged_lengths_equals_two_step(G, L, D):
+    """Tile edges of the fused AWGN + FIR kernel: odd and short streams, a single tap, a filter longer than a Philox
+    pair run, chunk boundaries (8 tiles of 2,048) -- always bit-identical to Noise followed by conv+truncate in FP32."""
+    import torch
+    ctx = G.default_context("f32")
+    rng = np.random.default_rng(L + D)
+    B = 2
+    x = ctx.cplx((rng.standard_normal((B, L)) + 1j * rng.standard_normal((B, L))))
+    h = np.zeros(D, dtype=complex)
+    nz = rng.choice(D, size=min(D, 5), replace=False)
+    h[nz] = rng.standard_normal(len(nz)) + 1j * rng.standard_normal(len(nz))
+    h[0] = 1.0
+    hd = ctx.cplx(h)
+    fused = ctx.channel_t5(x, snr_db=9.0, h_dev=hd, seed=3, first_stream_id=7)
+    two_step = ctx.channel_t5(ctx.channel_t5(x, snr_db=9.0, seed=3, first_stream_id=7), h_dev=hd)
+    assert torch.equal(torch.view_as_real(fused), torch.view_as_real(two_step))
+    normals = ctx.real(rng.standard_normal((B, 2, L)), ctx.rdtype)
+    fused_n = ctx.channel_t5(x, snr_db=9.0, h_dev=hd, normals_dev=normals)
+    two_step_n = ctx.channel_t5(ctx.channel_t5(x, snr_db=9.0, normals_dev=normals), h_dev=hd)
+    assert torch.equal(torch.view_as_real(fused_n), torch.view_as_real(two_step_n))
+
+
 def test_rx_chain_host_entry(G):
     import torch
     p = OC.params_task5(comb=4)

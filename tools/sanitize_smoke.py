@@ -20,8 +20,9 @@ lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF
 B = 3
 bits = ctx.bits(rng.integers(0, 2, B * p.stream_bits).astype(np.uint8))
 h, _ = O.get_MP_channel_resp([[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]], p.Nfft)
-tx = ctx.tx_chain(lp, bits, B)
-rx = ctx.channel_t5(tx, snr_db=20.0, h_dev=ctx.cplx(h), seed=1)
+tx, psum = ctx.tx_chain(lp, bits, B, want_power=True)
+rx = ctx.channel_t5(tx, snr_db=20.0, h_dev=ctx.cplx(h), seed=1, power_sum=psum)
+rx_own = ctx.channel_t5(tx, snr_db=20.0, h_dev=ctx.cplx(h), seed=1)
 r5 = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bits, near_eps=1e-3)
 # Task-4 shape: autocorrelation + warp-per-symbol chain
 p4 = OC.params_task4()
