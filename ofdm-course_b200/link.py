@@ -449,7 +449,12 @@ class Context:
     def channel_t5(self, tx_dev, snr_db=None, h_dev=None, normals_dev=None, seed=0, first_stream_id=0, out=None, power_sum=None):
         x = tx_dev.reshape(tx_dev.shape[0], -1)
         B, L = x.shape
-        s = self.real(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (B,)).copy()) if snr_db is not None else None
+        if snr_db is None:
+            s = None
+        elif np.ndim(snr_db) == 0 and not isinstance(snr_db, torch.Tensor):
+            s = torch.full((B,), float(snr_db), dtype=torch.float64, device=self.device)      # filled on the device: no host copy, no implicit sync
+        else:
+            s = self.real(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (B,)).copy())
         if out is None:
             out = torch.empty_like(x)
         D = h_dev.shape[-1] if h_dev is not None else 0

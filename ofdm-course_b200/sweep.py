@@ -48,21 +48,28 @@ def run_sweep(snrs_db, streams_per_point, block, compute, rank=0, world=1, devic
     return reduce_counts(torch.from_numpy(local), device).cpu().numpy()
 
 
-def ber_sweep_task5(ctx, lp, snrs_db, streams_per_point, block, taps_h, seed=1, rank=0, world=1, near_eps=0.0):
+def ber_sweep_task5(ctx, lp, snrs_db, streams_per_point, block, taps_h, seed=1, rank=0, world=1, near_eps=0.0, sync_every_item=False):
     """Full TX -> AWGN + multipath -> RX sweep on this rank's GPU (`ctx`), one fused kernel per stage and item.
     Payload bits and noise are keyed by the global stream id, so any (rank, world) split gives the same counts."""
     h_dev = ctx.cplx(np.asarray(taps_h)) if taps_h is not None else None
     words = lp.stream_bits // 32
+    snrs_db = list(snrs_db)
     n_snr = len(snrs_db)
 
-    def compute(i, snr_db, s0, n):
+    # Counters stay on the device (the RX kernel accumulates into the row of its SNR point) and are read once at the end:
+    # no host synchronisation between work items, so the launches of item k+1 are queued while item k runs.
+    acc = torch.zeros((n_snr, 3), dtype=torch.int64, device=ctx.device)
+    for (i, s0, n) in my_items(work_list(n_snr, streams_per_point, block), rank, world):
         gid0 = i * streams_per_point + s0                      # global stream id of the item's first stream
         gen = torch.Generator(device=ctx.device)
         gen.manual_seed(seed * 1_000_003 + gid0)
         bits = torch.randint(-2**31, 2**31 - 1, (n * words,), dtype=torch.int32, device=ctx.device, generator=gen)
         tx, psum = ctx.tx_chain(lp, bits, n, want_power=True)       # stream power measured in the TX kernel's registers
-        rx = ctx.channel_t5(tx, snr_db=float(snr_db), h_dev=h_dev, seed=seed, first_stream_id=gid0, power_sum=psum)
-        res = ctx.rx_chain_t5(lp, rx, n, tx_bits_dev=bits, want_bits=False, want_H=False, near_eps=near_eps)
-        return res["counts"].cpu().numpy()
-
-    return run_sweep(snrs_db, streams_per_point, block, compute, rank, world, ctx.device if world > 1 else None)
+        rx = ctx.channel_t5(tx, snr_db=float(snrs_db[i]), h_dev=h_dev, seed=seed, first_stream_id=gid0, power_sum=psum)
+        del tx
+        ctx.rx_chain_t5(lp, rx, n, tx_bits_dev=bits, want_bits=False, want_H=False, near_eps=near_eps, counts=acc[i])
+        del rx, bits, psum                                     # same stream: the allocator hands these blocks to the next item
+        if sync_every_item:
+            ctx.sync()
+    ctx.sync()
+    return reduce_counts(acc.cpu(), ctx.device if world > 1 else None).cpu().numpy()

@@ -40,13 +40,15 @@ def main():
     lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers, p.pilotCarriers, p.pilotValues)
     h, _ = O.get_MP_channel_resp([[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]], p.Nfft)
     snrs = np.arange(0.0, 30.0 + 1e-9, a.snr_step)
-    sweep.ber_sweep_task5(ctx, lp, snrs[:2], min(a.block, 1024), min(a.block, 1024), h, rank=rank, world=world)   # warm-up
+    # warm-up at the timed block size, so that the 4 GB signal buffers are already in the allocator's cache (a first cudaMalloc of
+    # that size costs tens of milliseconds -- a seventh of the whole sweep) and every kernel variant has been loaded
+    sweep.ber_sweep_task5(ctx, lp, snrs[:2 * world], min(a.block, a.streams_per_point), a.block, h, rank=rank, world=world)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     l0 = ctx.launches
-    res = sweep.ber_sweep_task5(ctx, lp, snrs, a.streams_per_point, a.block, h, rank=rank, world=world)
+    res = sweep.ber_sweep_task5(ctx, lp, snrs, a.streams_per_point, a.block, h, rank=rank, world=world, sync_every_item=bool(os.environ.get("OFDM_SWEEP_SYNC")))
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=ctx.device)
     if world > 1:
