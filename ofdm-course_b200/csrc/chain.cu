@@ -194,123 +194,123 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     };
     if ((int64_t)blockIdx.x < B) fetch_frame(blockIdx.x, 0);
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
-    double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
-    for (int f = 0; f < p.frames; ++f) {
-        const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
-        __syncthreads();                                   // previous frame's bit array is no longer read
+        double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
+        for (int f = 0; f < p.frames; ++f) {
+            const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+            __syncthreads();                                   // previous frame's bit array is no longer read
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int w = tid + CH_THREADS * j;
-            if (w < fw) s0[w] = (w == 0 && p.scramble) ? nb[j] ^ (p.prev0 >> 19) ^ (p.prev0 >> 18) : nb[j];   // fold the register pre-history into the input
-        }
-        for (int w = tid + 3 * CH_THREADS; w < fw; w += CH_THREADS) s0[w] = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
-        __syncthreads();
-        if (f + 1 < p.frames) fetch_frame(b, f + 1);
-        else if (b + gridDim.x < B) fetch_frame(b + gridDim.x, 0);
-        uint32_t* cur = s0; uint32_t* nxt = s1;
-        if (p.scramble) {
-            for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
-                if (((sh13 | sh14) & 31) == 0) {           // from the sixth doubling on both shifts are whole words
-                    const int d13 = sh13 >> 5, d14 = sh14 >> 5;
-                    for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ cur[w - d13] ^ cur[w - d14];
-                } else {                                   // bits [32w - sh, 32w - sh + 32) straddle words w - q - 1 and w - q (sh = 32 q + r); the words before the frame are the zero pad
-                    const int q13 = sh13 >> 5, r13 = sh13 & 31, q14 = sh14 >> 5, r14 = sh14 & 31;
-                    for (int w = tid; w < fw; w += CH_THREADS) {
-                        const int i13 = w - q13, i14 = w - q14;
-                        const uint32_t a = __funnelshift_l(cur[i13 - 1], cur[i13], r13);
-                        const uint32_t c = __funnelshift_l(cur[i14 - 1], cur[i14], r14);
-                        nxt[w] = cur[w] ^ a ^ c;
-                    }
-                }
-                __syncthreads();
-                uint32_t* t = cur; cur = nxt; nxt = t;
+            for (int j = 0; j < 3; ++j) {
+                const int w = tid + CH_THREADS * j;
+                if (w < fw) s0[w] = (w == 0 && p.scramble) ? nb[j] ^ (p.prev0 >> 19) ^ (p.prev0 >> 18) : nb[j];   // fold the register pre-history into the input
             }
-        }
-        for (int sf = 0; sf < p.SpF; ++sf) {
-            const int s = f * p.SpF + sf;
-            float2* X = xb + par * TXF_XBUF;
-            par ^= 1;
-            float2 v[16];
-            // ---- carriers of this thread, conjugated (mapping.m:14-21, OFDM_map_carriers.m:3-7).  Every lane runs the data path
-            // on a clamped slot and picks afterwards: a comb layout mixes data and pilot lanes in every warp.
-#pragma unroll
-            for (int m1 = 0; m1 < 4; ++m1) {
-                const int sl = slot4[m1];
-                const int qb = (sf * p.Nd + max(sl, 0)) * p.bps;
-                const uint32_t g = aligned ? cur[qb >> 5] >> (qb & 31) : sm_get32(cur, qb, fw);   // bps | 32: a group never straddles a word
-                const float2 cd = cs[__brev(g) >> (32 - p.bps)];      // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
-                v[m1] = sl >= 0 ? cd : (sl != SLOT_ZERO ? make_float2(pv[m1].x, -pv[m1].y) : make_float2(0.f, 0.f));
-            }
-            {                                                         // next symbol's pilot column (the next stream's first), in flight during the transform
-                const int sn = s + 1 < p.S ? s + 1 : 0;
-#pragma unroll
-                for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)sn * p.Np + pidx[m1]];
-            }
-            // ---- pass A (rows 4..15 of the column are empty)
-            fft16_in4(v);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const int q1 = c + 4 * d;
-                    float2 x = v[4 * c + d];
-                    if (q1) x = cmul(x, ta[q1]);
-                    X[q1 * 256 + tid] = x;
-                }
+            for (int w = tid + 3 * CH_THREADS; w < fw; w += CH_THREADS) s0[w] = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
             __syncthreads();
-            // ---- pass B
-            {
-                float2* rp = X + (tid >> 4) * 256 + (tid & 15);
+            if (f + 1 < p.frames) fetch_frame(b, f + 1);
+            else if (b + gridDim.x < B) fetch_frame(b + gridDim.x, 0);
+            uint32_t* cur = s0; uint32_t* nxt = s1;
+            if (p.scramble) {
+                for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
+                    if (((sh13 | sh14) & 31) == 0) {           // from the sixth doubling on both shifts are whole words
+                        const int d13 = sh13 >> 5, d14 = sh14 >> 5;
+                        for (int w = tid; w < fw; w += CH_THREADS) nxt[w] = cur[w] ^ cur[w - d13] ^ cur[w - d14];
+                    } else {                                   // bits [32w - sh, 32w - sh + 32) straddle words w - q - 1 and w - q (sh = 32 q + r); the words before the frame are the zero pad
+                        const int q13 = sh13 >> 5, r13 = sh13 & 31, q14 = sh14 >> 5, r14 = sh14 & 31;
+                        for (int w = tid; w < fw; w += CH_THREADS) {
+                            const int i13 = w - q13, i14 = w - q14;
+                            const uint32_t a = __funnelshift_l(cur[i13 - 1], cur[i13], r13);
+                            const uint32_t c = __funnelshift_l(cur[i14 - 1], cur[i14], r14);
+                            nxt[w] = cur[w] ^ a ^ c;
+                        }
+                    }
+                    __syncthreads();
+                    uint32_t* t = cur; cur = nxt; nxt = t;
+                }
+            }
+            for (int sf = 0; sf < p.SpF; ++sf) {
+                const int s = f * p.SpF + sf;
+                float2* X = xb + par * TXF_XBUF;
+                par ^= 1;
+                float2 v[16];
+                // ---- carriers of this thread, conjugated (mapping.m:14-21, OFDM_map_carriers.m:3-7).  Every lane runs the data path
+                // on a clamped slot and picks afterwards: a comb layout mixes data and pilot lanes in every warp.
 #pragma unroll
-                for (int m2 = 0; m2 < 16; ++m2) v[m2] = rp[16 * m2];
-                __syncthreads();
-                fft16(v);
-                float2* wp = X + (tid >> 4) * TXF_XROW + (tid & 15);
+                for (int m1 = 0; m1 < 4; ++m1) {
+                    const int sl = slot4[m1];
+                    const int qb = (sf * p.Nd + max(sl, 0)) * p.bps;
+                    const uint32_t g = aligned ? cur[qb >> 5] >> (qb & 31) : sm_get32(cur, qb, fw);   // bps | 32: a group never straddles a word
+                    const float2 cd = cs[__brev(g) >> (32 - p.bps)];      // first bit of the group is the index MSB (`mapping.m:18`, 'left-msb')
+                    v[m1] = sl >= 0 ? cd : (sl != SLOT_ZERO ? make_float2(pv[m1].x, -pv[m1].y) : make_float2(0.f, 0.f));
+                }
+                {                                                         // next symbol's pilot column (the next stream's first), in flight during the transform
+                    const int sn = s + 1 < p.S ? s + 1 : 0;
+#pragma unroll
+                    for (int m1 = 0; m1 < 4; ++m1) pv[m1] = p.pilots[(int64_t)sn * p.Np + pidx[m1]];
+                }
+                // ---- pass A (rows 4..15 of the column are empty)
+                fft16_in4(v);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
-                        const int q2 = c + 4 * d;
+                        const int q1 = c + 4 * d;
                         float2 x = v[4 * c + d];
-                        x = q2 ? cmul(x, tb[q2]) : make_float2(x.x * tb[0].x, x.y * tb[0].x);
-                        wp[16 * q2] = x;
+                        if (q1) x = cmul(x, ta[q1]);
+                        X[q1 * 256 + tid] = x;
                     }
-            }
-            __syncthreads();
-            // ---- pass C (all 16 outputs) + conj/N + cyclic prefix
-            {
-                const float4* rp = reinterpret_cast<const float4*>(X + (tid & 15) * TXF_XROW + (tid >> 4) * 16);
+                __syncthreads();
+                // ---- pass B
+                {
+                    float2* rp = X + (tid >> 4) * 256 + (tid & 15);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 w = rp[j];
-                    v[2 * j] = make_float2(w.x, w.y);
-                    v[2 * j + 1] = make_float2(w.z, w.w);
+                    for (int m2 = 0; m2 < 16; ++m2) v[m2] = rp[16 * m2];
+                    __syncthreads();
+                    fft16(v);
+                    float2* wp = X + (tid >> 4) * TXF_XROW + (tid & 15);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int d = 0; d < 4; ++d) {
+                            const int q2 = c + 4 * d;
+                            float2 x = v[4 * c + d];
+                            x = q2 ? cmul(x, tb[q2]) : make_float2(x.x * tb[0].x, x.y * tb[0].x);
+                            wp[16 * q2] = x;
+                        }
                 }
-            }
-            fft16(v);
-            float2* dst = out + (b * p.S + s) * (int64_t)(4096 + p.Tg);
-            const int cp0 = 4096 - p.Tg;
-            float psym = 0.f;
+                __syncthreads();
+                // ---- pass C (all 16 outputs) + conj/N + cyclic prefix
+                {
+                    const float4* rp = reinterpret_cast<const float4*>(X + (tid & 15) * TXF_XROW + (tid >> 4) * 16);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    const int q3 = c + 4 * d;
-                    const int n = tid + 256 * q3;
-                    const float2 y = make_float2(v[4 * c + d].x, -v[4 * c + d].y);
-                    dst[p.Tg + n] = y;
-                    if (n >= cp0) dst[n - cp0] = y;
-                    const float e = y.x * y.x + y.y * y.y;
-                    psym += n >= cp0 ? e + e : e;
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 w = rp[j];
+                        v[2 * j] = make_float2(w.x, w.y);
+                        v[2 * j + 1] = make_float2(w.z, w.w);
+                    }
                 }
-            pacc += (double)psym;
+                fft16(v);
+                float2* dst = out + (b * p.S + s) * (int64_t)(4096 + p.Tg);
+                const int cp0 = 4096 - p.Tg;
+                float psym = 0.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int q3 = c + 4 * d;
+                        const int n = tid + 256 * q3;
+                        const float2 y = make_float2(v[4 * c + d].x, -v[4 * c + d].y);
+                        dst[p.Tg + n] = y;
+                        if (n >= cp0) dst[n - cp0] = y;
+                        const float e = y.x * y.x + y.y * y.y;
+                        psym += n >= cp0 ? e + e : e;
+                    }
+                pacc += (double)psym;
+            }
         }
-    }
-    if (power) {                                           // `Noise.m:3` needs mean |x|^2 of the stream: hand the sum to the channel stage
-        __shared__ double red[32];
-        const double tot = block_sum(pacc, red);
-        if (tid == 0) power[b] = tot;
-    }
+        if (power) {                                           // `Noise.m:3` needs mean |x|^2 of the stream: hand the sum to the channel stage
+            __shared__ double red[32];
+            const double tot = block_sum(pacc, red);
+            if (tid == 0) power[b] = tot;
+        }
     }
 }
 
