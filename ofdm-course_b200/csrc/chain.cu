@@ -181,7 +181,6 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     __shared__ float2 cs[16];                             // conjugated constellation (a divergent constant-bank index would serialise)
     if (tid < 16) cs[tid] = make_float2(p.con.re[tid], -p.con.im[tid]);
     int par = 0;
-    // persistent CTA: the per-thread twiddles, slot roles and the constellation table are set up once for all its streams
     // the payload words of the next frame are requested while the current one is transformed (three per thread cover 24,576-bit frames)
     uint32_t nb[3] = {0u, 0u, 0u};
     auto fetch_frame = [&](int64_t bb, int ff) {
@@ -193,6 +192,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
         }
     };
     if ((int64_t)blockIdx.x < B) fetch_frame(blockIdx.x, 0);
+    // persistent CTA: the per-thread twiddles, slot roles and the constellation table above are set up once for all its streams
     for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
         double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
         for (int f = 0; f < p.frames; ++f) {
