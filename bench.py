@@ -186,8 +186,8 @@ def run_gpu(args, rank, world, local_rank):
     counts = torch.zeros(3, dtype=torch.int64, device=dev)
     torch.cuda.synchronize()
 
-    def step():
-        ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=tx_bits, out_bits=out_bits, H=H, counts=counts)
+    def step(eps=args.near_eps):
+        ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=tx_bits, out_bits=out_bits, H=H, counts=counts, near_eps=eps)
 
     def barrier():
         if world > 1:
@@ -227,6 +227,16 @@ def run_gpu(args, rank, world, local_rank):
     syms_per_step = B * S
     value = world * syms_per_step * args.steps / (total_ms * 1e-3)
     cnt = counts.cpu().numpy()
+    # the same kernel without the near-boundary counter (NEAR = false instantiation), for the cost of the counting
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step(0.0)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(max(3, args.steps // 4)):
+        step(0.0)
+    e1.record()
+    torch.cuda.synchronize()
+    near_off_ms = e0.elapsed_time(e1) / max(3, args.steps // 4)
 
     # ---- e2e: host buffers through the C-ABI host entry (H2D of rx + tx bits, D2H of bits + H + counters)
     Be = min(B, args.e2e_streams)
@@ -243,7 +253,7 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        c_host = ctx.rx_chain_t5_host(lp, rx_h, Be, tb_h, ob_h, H_h, chunk=args.e2e_chunk)
+        c_host = ctx.rx_chain_t5_host(lp, rx_h, Be, tb_h, ob_h, H_h, chunk=args.e2e_chunk, near_eps=args.near_eps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -267,14 +277,17 @@ def run_gpu(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "symbols_per_step_per_gpu": syms_per_step,
                    "input_bytes_per_gpu": int(rx.numel() * 8), "l2_policy": "inputs (33.8 GB at the default batch) larger than L2; no flush needed",
                    "noise": "Philox4x32-10 keyed by global stream id", "e2e_streams": Be, "e2e_chunk_streams": args.e2e_chunk,
-                   "ber": float(cnt[0]) / max(float(cnt[1]), 1.0)},
+                   "ber": float(cnt[0]) / max(float(cnt[1]), 1.0),
+                   "near_eps": args.near_eps, "near_boundary_symbols_per_step": int(cnt[2]) // max(args.steps, 1) // world,
+                   "data_symbols_per_step": int(cnt[1]) // 4 // max(args.steps, 1) // world,
+                   "ms_per_step_without_near_counter": near_off_ms},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_val, "unit": "symbols/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ((traffic or {}).get("dram_bytes_per_symbol") or 0) * syms_per_step or None, "peak_source": peak_src,
                      "traffic_source": (traffic or {}).get("source"),
-                     "kernel": "rx4096_kernel<true>", "algorithmic_bytes_per_symbol": A_M1, "kernel_ms": k_ms},
+                     "kernel": "rx4096_kernel<NEAR=%s>" % ("true" if args.near_eps > 0 else "false"), "algorithmic_bytes_per_symbol": A_M1, "kernel_ms": k_ms},
     }
     if world == 1 and not args.no_cpu:
         n_proc = os.cpu_count() or 1
@@ -296,6 +309,8 @@ def main():
     ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--ref-streams", type=int, default=200, help="distinct streams per host process in the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="RX-chain time per host process in the CPU sample")
+    ap.add_argument("--near-eps", type=float, default=1e-4,
+                    help="squared-distance margin below which a decision counts as 'within epsilon of a boundary' (0 = counter off)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup

@@ -268,6 +268,11 @@ OFDM_API int ofdm_rx_chain_t5(ofdm_ctx*, const ofdm_link_params*, const void* rx
 OFDM_API int ofdm_rx_chain_t5_host(ofdm_ctx*, const ofdm_link_params*, const void* rx_host, int64_t B,
                                    const uint32_t* tx_bits_host, uint32_t* out_bits_host, void* H_host,
                                    int64_t* counts_host, int64_t chunk_streams);
+/* Same with the near-boundary counter switched on: counts_host[2] = symbols whose two smallest squared distances to the
+ * constellation differ by less than near_eps (the "within epsilon of a decision boundary" count of the parity contract). */
+OFDM_API int ofdm_rx_chain_t5_host_eps(ofdm_ctx*, const ofdm_link_params*, const void* rx_host, int64_t B,
+                                       const uint32_t* tx_bits_host, uint32_t* out_bits_host, void* H_host,
+                                       int64_t* counts_host, int64_t chunk_streams, double near_eps);
 
 /* M2 RX chain, fused (FP32 contexts): AutoCorrFunction -> add_STO x2 -> add_CFO -> remove_IFO -> OFDM_demodulator ->
  * fine_sync -> estimate_channel -> equalize_signal -> get_payload -> demapping -> DeScrambler -> BER count

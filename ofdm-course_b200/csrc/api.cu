@@ -95,9 +95,11 @@ extern "C" void ofdm_ctx_destroy(ofdm_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (auto& kv : ctx->blob_cache) cudaFree(kv.second);
+    for (auto& kv : ctx->blob_cache) cudaFree(kv.second.dev);
+    for (auto& kv : ctx->blob_retired) cudaFree(kv.second.dev);
     for (auto& kv : ctx->twiddle_cache) cudaFree(kv.second);
     for (auto& kv : ctx->plan_cache) { cudaFree(kv.second.band); cudaFree(kv.second.qw); cudaFree(kv.second.qk); }
+    for (auto& kv : ctx->plan_retired) { cudaFree(kv.second.band); cudaFree(kv.second.qw); cudaFree(kv.second.qk); }
     for (void* p : ctx->owned) cudaFree(p);
     if (ctx->scratch) cudaFree(ctx->scratch);
     for (int i = 0; i < 2; ++i) { if (ctx->staging[i]) cudaFree(ctx->staging[i]); if (ctx->copy_stream[i]) cudaStreamDestroy(ctx->copy_stream[i]); }
@@ -158,19 +160,47 @@ extern "C" int ofdm_host_alloc(void** host, size_t bytes) {
 extern "C" int ofdm_host_free(void* host) { return cudaFreeHost(host) == cudaSuccess ? OFDM_OK : OFDM_ERR_CUDA; }
 
 // ---------------------------------------------------------------- caches
+// Table uploads come from pageable host memory.  cudaMemcpy may return once the data sits in the driver's staging buffer,
+// i.e. before the DMA lands, and the kernels that read the tables run on cudaStreamNonBlocking streams that are not
+// ordered against the legacy stream -- so every upload is followed by a synchronisation of the legacy stream (a one-time
+// cost per cached table).
+cudaError_t ctx_upload(void* dev, const void* host, size_t bytes) {
+    cudaError_t e = cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(cudaStreamLegacy);
+}
+
+// Cached upload of a small host blob, keyed by a 64-bit content hash and confirmed by the size and a second,
+// independent hash (a mismatch probes the next key).  The cache is bounded in two generations: when the live map
+// overflows it becomes the retired generation and the PREVIOUS retired generation is freed, so a pointer handed out
+// earlier in the same API call (calls take a handful of blobs in sequence) is never freed under the caller.
 void* ctx_blob(ofdm_ctx* ctx, const void* host, size_t bytes) {
     uint64_t key = fnv1a(host, bytes) ^ (uint64_t)bytes * 0x9E3779B97F4A7C15ull;
-    auto it = ctx->blob_cache.find(key);
-    if (it != ctx->blob_cache.end()) return it->second;
-    if (ctx->blob_cache.size() > 4096) {  // bounded: drop everything (cudaFree synchronises)
-        for (auto& kv : ctx->blob_cache) cudaFree(kv.second);
-        ctx->blob_cache.clear();
+    const uint64_t check = fnv1a(host, bytes, 0x84222325CBF29CE4ull);
+    for (int probe = 0; probe < 8; ++probe, ++key) {
+        auto it = ctx->blob_cache.find(key);
+        if (it == ctx->blob_cache.end()) {
+            auto rt = ctx->blob_retired.find(key);
+            if (rt == ctx->blob_retired.end()) break;                      // free key: upload below
+            if (rt->second.bytes == bytes && rt->second.check == check) {  // still alive in the retired generation
+                ctx->blob_cache[key] = rt->second;
+                void* d = rt->second.dev;
+                ctx->blob_retired.erase(rt);
+                return d;
+            }
+            continue;
+        }
+        if (it->second.bytes == bytes && it->second.check == check) return it->second.dev;
+    }
+    if (ctx->blob_cache.size() >= OFDM_BLOB_CACHE_LIMIT) {
+        for (auto& kv : ctx->blob_retired) cudaFree(kv.second.dev);       // cudaFree waits for kernels still reading them
+        ctx->blob_retired.clear();
+        ctx->blob_retired.swap(ctx->blob_cache);
     }
     void* d = nullptr;
     if (cudaMalloc(&d, bytes ? bytes : 1) != cudaSuccess) return nullptr;
-    // synchronous copy: `host` may be a caller temporary
-    if (cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
-    ctx->blob_cache[key] = d;
+    if (ctx_upload(d, host, bytes) != cudaSuccess) { cudaFree(d); return nullptr; }
+    ctx->blob_cache[key] = BlobEntry{d, bytes, check};
     return d;
 }
 
@@ -192,12 +222,12 @@ const void* ctx_twiddles(ofdm_ctx* ctx, int N) {
         std::vector<double2> t(N);
         for (int k = 0; k < N; ++k) { long double a = -2.0L * M_PIl * k / N; t[k] = make_double2((double)cosl(a), (double)sinl(a)); }
         if (cudaMalloc(&d, sizeof(double2) * N) != cudaSuccess) return nullptr;
-        cudaMemcpy(d, t.data(), sizeof(double2) * N, cudaMemcpyHostToDevice);
+        if (ctx_upload(d, t.data(), sizeof(double2) * N) != cudaSuccess) { cudaFree(d); return nullptr; }
     } else {
         std::vector<float2> t(N);
         for (int k = 0; k < N; ++k) { long double a = -2.0L * M_PIl * k / N; t[k] = make_float2((float)cosl(a), (float)sinl(a)); }
         if (cudaMalloc(&d, sizeof(float2) * N) != cudaSuccess) return nullptr;
-        cudaMemcpy(d, t.data(), sizeof(float2) * N, cudaMemcpyHostToDevice);
+        if (ctx_upload(d, t.data(), sizeof(float2) * N) != cudaSuccess) { cudaFree(d); return nullptr; }
     }
     ctx->twiddle_cache[key] = d;
     return d;
@@ -266,6 +296,8 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
     if (queries1) key = fnv1a(queries1, sizeof(int32_t) * nq, key);
     auto it = ctx->plan_cache.find(key);
     if (it != ctx->plan_cache.end()) return &it->second;
+    it = ctx->plan_retired.find(key);
+    if (it != ctx->plan_retired.end()) return &it->second;
 
     InterpPlan p;
     memset(&p, 0, sizeof p);
@@ -359,19 +391,27 @@ const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_
         void* d = nullptr;
         if (ctx->precision == OFDM_PREC_F64) {
             if (cudaMalloc(&d, v.size() * sizeof(double) + 8) != cudaSuccess) return nullptr;
-            cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+            if (ctx_upload(d, v.data(), v.size() * sizeof(double)) != cudaSuccess) { cudaFree(d); return nullptr; }
         } else {
             std::vector<float> f(v.begin(), v.end());
             if (cudaMalloc(&d, f.size() * sizeof(float) + 8) != cudaSuccess) return nullptr;
-            cudaMemcpy(d, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice);
+            if (ctx_upload(d, f.data(), f.size() * sizeof(float)) != cudaSuccess) { cudaFree(d); return nullptr; }
         }
         return d;
     };
     p.band = upload_real(band);
     p.qw = upload_real(qw);
-    if (cudaMalloc((void**)&p.qk, sizeof(int32_t) * nq + 8) != cudaSuccess) return nullptr;
-    cudaMemcpy(p.qk, qk.data(), sizeof(int32_t) * nq, cudaMemcpyHostToDevice);
-    if (!p.band || !p.qw) return nullptr;
+    if (p.band && p.qw && cudaMalloc((void**)&p.qk, sizeof(int32_t) * nq + 8) != cudaSuccess) p.qk = nullptr;
+    if (!p.band || !p.qw || !p.qk || ctx_upload(p.qk, qk.data(), sizeof(int32_t) * nq) != cudaSuccess) {
+        cudaFree(p.band); cudaFree(p.qw); cudaFree(p.qk);
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (ctx->plan_cache.size() >= OFDM_PLAN_CACHE_LIMIT) {   // two generations, as for the blobs: plans returned earlier in this call stay valid
+        for (auto& kv : ctx->plan_retired) { cudaFree(kv.second.band); cudaFree(kv.second.qw); cudaFree(kv.second.qk); }
+        ctx->plan_retired.clear();
+        ctx->plan_retired.swap(ctx->plan_cache);              // std::map::swap keeps element addresses
+    }
     ctx->plan_cache[key] = p;
     return &ctx->plan_cache[key];
 }

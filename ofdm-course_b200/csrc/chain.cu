@@ -476,6 +476,11 @@ extern "C" int ofdm_rx_chain_t5(ofdm_ctx* ctx, const ofdm_link_params* lp, const
 // ------------------------------------------------------------------------------------ RX from host buffers
 extern "C" int ofdm_rx_chain_t5_host(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx_host, int64_t B, const uint32_t* tx_bits_host,
                                      uint32_t* out_bits_host, void* H_host, int64_t* counts_host, int64_t chunk) {
+    return ofdm_rx_chain_t5_host_eps(ctx, lp, rx_host, B, tx_bits_host, out_bits_host, H_host, counts_host, chunk, 0.0);
+}
+
+extern "C" int ofdm_rx_chain_t5_host_eps(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx_host, int64_t B, const uint32_t* tx_bits_host,
+                                         uint32_t* out_bits_host, void* H_host, int64_t* counts_host, int64_t chunk, double near_eps) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, rx_host && lp && B >= 0 && counts_host, "bad argument");
     ConstTable ct = host_constellation(lp->constellation);
@@ -499,15 +504,24 @@ extern "C" int ofdm_rx_chain_t5_host(ofdm_ctx* ctx, const ofdm_link_params* lp, 
         for (int i = 0; i < 2; ++i) CUDA_TRY(ctx, cudaMalloc(&ctx->staging[i], slot_b));
         ctx->staging_bytes = slot_b;
     }
-    int64_t* counts_d = nullptr;
-    CUDA_TRY(ctx, cudaMalloc((void**)&counts_d, 3 * sizeof(int64_t)));
-    CUDA_TRY(ctx, cudaMemsetAsync(counts_d, 0, 3 * sizeof(int64_t), ctx->stream));
+    // the three counters live in the context (allocated once): no cudaMalloc/cudaFree, both device-synchronising, per call
+    if (!ctx->host_counts_d) {
+        CUDA_TRY(ctx, cudaMalloc((void**)&ctx->host_counts_d, 64));
+        ctx->owned.push_back(ctx->host_counts_d);
+    }
+    int64_t* counts_d = ctx->host_counts_d;
     cudaStream_t user = ctx->stream;
     cudaEvent_t done[2] = {ctx->ev[0], ctx->ev[1]};
-    CUDA_TRY(ctx, cudaEventRecord(ctx->ev[2], user));
-    for (int i = 0; i < 2; ++i) CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->copy_stream[i], ctx->ev[2], 0));
     int rc = OFDM_OK;
-    int64_t launches = 0;
+    // one exit path: CUDA failures inside the chunk loop fall through to the drain below instead of returning with copies in flight
+#define HOST_TRY(expr)                                                                                                              \
+    do {                                                                                                                            \
+        cudaError_t _e = (expr);                                                                                                    \
+        if (_e != cudaSuccess && rc == OFDM_OK) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+    HOST_TRY(cudaMemsetAsync(counts_d, 0, 3 * sizeof(int64_t), user));
+    HOST_TRY(cudaEventRecord(ctx->ev[2], user));
+    for (int i = 0; i < 2; ++i) HOST_TRY(cudaStreamWaitEvent(ctx->copy_stream[i], ctx->ev[2], 0));
     for (int64_t c0 = 0, it = 0; c0 < B && rc == OFDM_OK; c0 += chunk, ++it) {
         const int slot = (int)(it & 1);
         const int64_t nb = std::min(chunk, B - c0);
@@ -517,25 +531,25 @@ extern "C" int ofdm_rx_chain_t5_host(ofdm_ctx* ctx, const ofdm_link_params* lp, 
         uint32_t* tx_d = (uint32_t*)(base + rx_b);
         uint32_t* ob_d = (uint32_t*)(base + rx_b + bits_b);
         void* H_d = base + rx_b + 2 * bits_b;
-        CUDA_TRY(ctx, cudaMemcpy2DAsync(rx_d, esz * lp->Nfft, (const unsigned char*)rx_host + esz * (L * c0 + lp->Tg), esz * (lp->Nfft + lp->Tg), esz * lp->Nfft,
-                                        (size_t)nb * lp->S, cudaMemcpyHostToDevice, st));
-        if (tx_bits_host) CUDA_TRY(ctx, cudaMemcpyAsync(tx_d, tx_bits_host + words * c0, sizeof(uint32_t) * words * nb, cudaMemcpyHostToDevice, st));
+        HOST_TRY(cudaMemcpy2DAsync(rx_d, esz * lp->Nfft, (const unsigned char*)rx_host + esz * (L * c0 + lp->Tg), esz * (lp->Nfft + lp->Tg), esz * lp->Nfft,
+                                   (size_t)nb * lp->S, cudaMemcpyHostToDevice, st));
+        if (tx_bits_host) HOST_TRY(cudaMemcpyAsync(tx_d, tx_bits_host + words * c0, sizeof(uint32_t) * words * nb, cudaMemcpyHostToDevice, st));
+        if (rc) break;
         ctx->stream = st;
-        int64_t l0 = ctx->launches;
-        rc = ofdm_rx_chain_t5(ctx, &lpd, rx_d, nb, tx_bits_host ? tx_d : nullptr, out_bits_host ? ob_d : nullptr, H_host ? H_d : nullptr, counts_d, nullptr, 0.0);
-        launches += ctx->launches - l0;
+        rc = ofdm_rx_chain_t5(ctx, &lpd, rx_d, nb, tx_bits_host ? tx_d : nullptr, out_bits_host ? ob_d : nullptr, H_host ? H_d : nullptr, counts_d, nullptr, near_eps);
         ctx->stream = user;
         if (rc) break;
-        if (out_bits_host) CUDA_TRY(ctx, cudaMemcpyAsync(out_bits_host + words * c0, ob_d, sizeof(uint32_t) * words * nb, cudaMemcpyDeviceToHost, st));
-        if (H_host) CUDA_TRY(ctx, cudaMemcpyAsync((unsigned char*)H_host + esz * lp->N_carrier * c0, H_d, esz * lp->N_carrier * nb, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(ctx, cudaEventRecord(done[slot], st));
+        if (out_bits_host) HOST_TRY(cudaMemcpyAsync(out_bits_host + words * c0, ob_d, sizeof(uint32_t) * words * nb, cudaMemcpyDeviceToHost, st));
+        if (H_host) HOST_TRY(cudaMemcpyAsync((unsigned char*)H_host + esz * lp->N_carrier * c0, H_d, esz * lp->N_carrier * nb, cudaMemcpyDeviceToHost, st));
+        HOST_TRY(cudaEventRecord(done[slot], st));
     }
-    for (int i = 0; i < 2; ++i) { cudaStreamSynchronize(ctx->copy_stream[i]); }
-    (void)launches;
+    // join: slot 1 waits for slot 0, reads the counters back, and the host waits for slot 1 only
     if (rc == OFDM_OK) {
-        cudaError_t e = cudaMemcpy(counts_host, counts_d, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "counter read-back failed: %s", cudaGetErrorString(e));
+        HOST_TRY(cudaEventRecord(done[0], ctx->copy_stream[0]));
+        HOST_TRY(cudaStreamWaitEvent(ctx->copy_stream[1], done[0], 0));
+        HOST_TRY(cudaMemcpyAsync(counts_host, counts_d, 3 * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->copy_stream[1]));
     }
-    cudaFree(counts_d);
+    for (int i = 0; i < 2; ++i) HOST_TRY(cudaStreamSynchronize(ctx->copy_stream[i]));
+#undef HOST_TRY
     return rc;
 }

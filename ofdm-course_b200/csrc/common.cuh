@@ -175,6 +175,10 @@ struct InterpPlan {       // device-resident spline/linear operator for a fixed 
     int32_t* qk;          // nq interval index
 };
 
+struct BlobEntry { void* dev; size_t bytes; uint64_t check; };
+#define OFDM_BLOB_CACHE_LIMIT 4096
+#define OFDM_PLAN_CACHE_LIMIT 512
+
 struct ofdm_ctx {
     int device = 0;
     int precision = OFDM_PREC_F32;
@@ -185,18 +189,21 @@ struct ofdm_ctx {
     int sm_count = 148;
     int64_t launches = 0;
     std::string err;
-    std::map<uint64_t, void*> blob_cache;          // small host config blobs mirrored on device
-    std::map<uint64_t, void*> twiddle_cache;       // key = N<<1 | prec
-    std::map<uint64_t, InterpPlan> plan_cache;
+    std::map<uint64_t, BlobEntry> blob_cache;      // small host config blobs mirrored on device (live generation)
+    std::map<uint64_t, BlobEntry> blob_retired;    // previous generation: freed when the live one overflows again
+    std::map<uint64_t, void*> twiddle_cache;       // key = N<<1 | prec (N a power of two <= 8192: bounded by construction)
+    std::map<uint64_t, InterpPlan> plan_cache, plan_retired;
     std::vector<void*> owned;                      // freed at destroy
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
     void* staging[2] = {nullptr, nullptr};         // device staging for the *_host chain
     size_t staging_bytes = 0;
+    int64_t* host_counts_d = nullptr;              // {errors, bits, near} of the *_host chain (in `owned`)
 };
 
 int ctx_fail(ofdm_ctx* ctx, int code, const char* fmt, ...);
 void* ctx_blob(ofdm_ctx* ctx, const void* host, size_t bytes);           // cached upload (by content hash)
+cudaError_t ctx_upload(void* dev, const void* host, size_t bytes);       // pageable H2D, complete on return
 void* ctx_scratch(ofdm_ctx* ctx, size_t bytes);                          // grow-only scratch
 const void* ctx_twiddles(ofdm_ctx* ctx, int N);                          // W_N^k, k=0..N-1, ctx precision
 const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_to /*0=no ext*/,

@@ -254,7 +254,7 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
     REQUIRE(ctx, rx && tg_pos && freq_off && B >= 0 && W > 0 && Nfft > 0, "bad argument");
     const int64_t n_out = L - W - Nfft;
     REQUIRE(ctx, n_out >= 65, "stream too short for AutoCorrFunction (needs L-W-Nfft >= 65)");
-    REQUIRE(ctx, W <= 2048, "window wider than 2048 samples");
+    REQUIRE(ctx, W <= 1536, "window wider than 1536 samples (the tile of 16*(126 - W/16) outputs per block must stay positive)");
     if (B == 0) return OFDM_OK;
     const int64_t flag_words = (n_out + 31) / 32;
     uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words);

@@ -532,12 +532,13 @@ class Context:
         return {"bits": out_bits, "counts": counts, "TgPosition": tg, "FreqOffset": fo, "IFO": ifo, "tau": tau, "phase_shift": ph, "H": H,
                 "near": counts[2]}
 
-    def rx_chain_t5_host(self, lp, rx_host, B, tx_bits_host=None, out_bits_host=None, H_host=None, chunk=2048):
-        """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Returns counts (3 int64)."""
+    def rx_chain_t5_host(self, lp, rx_host, B, tx_bits_host=None, out_bits_host=None, H_host=None, chunk=2048, near_eps=0.0):
+        """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Returns counts (3 int64:
+        errors, bits, symbols within ``near_eps`` of a decision boundary)."""
         counts = np.zeros(3, dtype=np.int64)
         hp = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
-        self._chk(self.lib.ofdm_rx_chain_t5_host(self.h, C.byref(lp), hp(rx_host), B, hp(tx_bits_host), hp(out_bits_host), hp(H_host),
-                                                 counts.ctypes.data_as(C.c_void_p), chunk))
+        self._chk(self.lib.ofdm_rx_chain_t5_host_eps(self.h, C.byref(lp), hp(rx_host), B, hp(tx_bits_host), hp(out_bits_host), hp(H_host),
+                                                     counts.ctypes.data_as(C.c_void_p), chunk, float(near_eps)))
         return counts
 
 
