@@ -212,6 +212,7 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(counts)             # the chain's only collective: int64 error / bit counters
     barrier()
     launches = ctx.launches - l0
+    cnt = counts.cpu().numpy()              # counters of exactly the timed steps
     total_ms = ev[0].elapsed_time(ev[-1])
     kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     if world > 1:
@@ -226,7 +227,6 @@ def run_gpu(args, rank, world, local_rank):
     sampler.stop_flag = True
     syms_per_step = B * S
     value = world * syms_per_step * args.steps / (total_ms * 1e-3)
-    cnt = counts.cpu().numpy()
     # the same kernel without the near-boundary counter (NEAR = false instantiation), for the cost of the counting
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     step(0.0)

@@ -1,7 +1,7 @@
 // Fast path of the M1 RX chain: Nfft = 4096, N_carrier <= 1024, FP32.
 //
 // One persistent CTA of 256 threads walks whole streams.  Per OFDM symbol:
-//   global (CP skipped, 8-byte coalesced loads, 16 in flight per thread)
+//   global -> shared by one 32 KB bulk copy per symbol (TMA engine, CP skipped, two symbols in flight)
 //   -> radix-16 pass A in registers -> shared exchange -> pass B -> shared exchange
 //   -> pass C pruned to the 1,024 consumed bins (k3 < 4)   [OFDM_demodulator.m:5-8]
 //   -> symbol 0 only: pilot LS + edge extension + banded spline operator   [LS_CE.m:27-31]
@@ -72,10 +72,22 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // prefetched two items ahead into a two-buffer ring by one elected thread; all three FFT passes run
 // in place in the buffer the symbol landed in:
 //   pass A  x[256 n1 + t]            -> same places, index k1 replaces n1          (thread-private)
-//   pass B  [256 k1 + 16 n2 + n3]    -> [258 k1 + 16 k2 + n3]                        (row pad of two samples)
+//   pass B  [256 k1 + 16 n2 + n3]    -> [XROW k1 + XGRP k2 + n3]  (XROW 288, XGRP 18: two pad samples per group of 16)
 //   pass C  reads 16 consecutive n3 per (k1,k2) as eight 128-bit loads with immediate offsets: conflict-free
-//           because of the pad (129 k1 mod 8 is a permutation over a quarter warp).
-template <bool QAM16, bool NEAR>
+//           because of the pad ((9 k2 + j) mod 8 is a permutation over a quarter warp).
+// MASK (16 bits, one per k1 = k mod 16): rows of the pass-A output whose carriers {k1 + 16 j} hold no data carrier
+// (pilots or unused only).  The channel is estimated from symbol 0 alone (`LS_CE.m:27-28`), so on symbols 1..S-1
+// those rows are dead: pass A neither finishes nor stores them and the pass-B warps that own them idle (a comb-4
+// layout has MASK 0x1111: a quarter of passes A/B and of their shared-memory traffic).  Symbol 0 runs in full.
+__host__ __device__ constexpr int mask_popc(int m) { int n = 0; for (int i = 0; i < 16; ++i) n += (m >> i) & 1; return n; }
+// j-th row of the pass-B order: the pruned rows first (so they fill whole warps), then the others, each ascending
+__host__ __device__ constexpr int mask_perm(int m, int j) {
+    int n = 0;
+    for (int i = 0; i < 16; ++i) if ((m >> i) & 1) { if (n == j) return i; ++n; }
+    for (int i = 0; i < 16; ++i) if (!((m >> i) & 1)) { if (n == j) return i; ++n; }
+    return 0;
+}
+template <bool QAM16, bool NEAR, int MASK>
 __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
@@ -113,6 +125,9 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     // pass-C coordinates of this thread and its carriers kq + 256 c
     const int k1c = (tid >> 6) + 4 * ((tid >> 3) & 3), k2c = ((tid >> 5) & 1) * 8 + (tid & 7);
     const int kq = k1c + 16 * k2c;
+    // pass-B row of this thread and whether its warp owns pruned rows only
+    const int k1b = mask_perm(MASK, tid >> 4);
+    const bool b_idle = 2 * (tid >> 5) + 1 < mask_popc(MASK);
     // per-thread carrier roles (fixed for the whole kernel): data rank or 0xFFFF, two per register
     uint32_t role01, role23;
     bool warp_data, warp_pil;
@@ -165,34 +180,59 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
         // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, in place
-        fft16(v);
+        const bool pruned = MASK != 0 && s != 0;   // CTA-uniform
+        if (pruned) {
+            fft16_steps12(v);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const int k1 = c + 4 * d;
-                float2 x = v[4 * c + d];
-                if (k1) x = cmul(x, ta[k1]);
-                X[k1 * 256 + tid] = x;
-            }
-        __syncthreads();
-        // ---- pass B: thread (k1 = tid>>4, n3 = tid&15), DFT over n2, swizzled write-back
-        {
-            float2* rp = X + (tid >> 4) * 256 + (tid & 15);
-#pragma unroll
-            for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
-            __syncthreads();                       // every read precedes the swizzled writes
-            fft16(v);
-            float2* wp = X + (tid >> 4) * XROW + (tid & 15);
+            for (int c = 0; c < 4; ++c)
+                if (((MASK >> c) & 0x1111) != 0x1111) fft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
-                    const int k2 = c + 4 * d;
-                    float2 x = v[4 * c + d];
-                    if (k2) x = cmul(x, tb[k2]);
-                    wp[XGRP * k2] = x;
+                    const int k1 = c + 4 * d;
+                    if (!((MASK >> k1) & 1)) {
+                        float2 x = v[4 * c + d];
+                        if (k1) x = cmul(x, ta[k1]);
+                        X[k1 * 256 + tid] = x;
+                    }
                 }
+        } else {
+            fft16(v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    const int k1 = c + 4 * d;
+                    float2 x = v[4 * c + d];
+                    if (k1) x = cmul(x, ta[k1]);
+                    X[k1 * 256 + tid] = x;
+                }
+        }
+        __syncthreads();
+        // ---- pass B: thread (k1 = k1b, n3 = tid&15), DFT over n2, swizzled write-back; a warp whose two rows are
+        // pruned only keeps the barriers company
+        const bool b_active = !(pruned && b_idle);
+        {
+            float2* rp = X + k1b * 256 + (tid & 15);
+            if (b_active) {
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) v[n2] = rp[16 * n2];
+            }
+            __syncthreads();                       // every read precedes the swizzled writes
+            if (b_active) {
+                fft16(v);
+                float2* wp = X + k1b * XROW + (tid & 15);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int d = 0; d < 4; ++d) {
+                        const int k2 = c + 4 * d;
+                        float2 x = v[4 * c + d];
+                        if (k2) x = cmul(x, tb[k2]);
+                        wp[XGRP * k2] = x;
+                    }
+            }
         }
         __syncthreads();
         // ---- pass C: thread (k1c, k2c) -- a quarter warp holds eight consecutive k2 of one k1 (conflict-free 128-bit
@@ -361,9 +401,16 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
     const bool q16 = lp->constellation == OFDM_16QAM;
     const bool near = near_eps > 0.0;
+    // rows k1 = k mod 16 of the pass-A output that carry no data carrier: dead after symbol 0
+    int dead = 0xFFFF;
+    for (int k = 0; k < 1024; ++k) if (slot[k] >= 0) dead &= ~(1 << (k & 15));
+    if (getenv("OFDM_B200_NO_PRUNE")) dead = 0;
     typedef void (*kern_t)(Fast4096Params, PlanDev<float>, DevConst<float>, const float2*, int64_t, const uint32_t*, uint32_t*, float2*, unsigned long long*,
                            int32_t*, float);
-    kern_t kern = q16 ? (near ? rx4096_kernel<true, true> : rx4096_kernel<true, false>) : (near ? rx4096_kernel<false, true> : rx4096_kernel<false, false>);
+    kern_t kern;
+    if (q16 && (dead & 0x1111) == 0x1111) kern = near ? rx4096_kernel<true, true, 0x1111> : rx4096_kernel<true, false, 0x1111>;     // comb 4, 4m
+    else if (q16 && (dead & 0x0101) == 0x0101) kern = near ? rx4096_kernel<true, true, 0x0101> : rx4096_kernel<true, false, 0x0101>;  // comb 8, 8m
+    else kern = q16 ? (near ? rx4096_kernel<true, true, 0> : rx4096_kernel<true, false, 0>) : (near ? rx4096_kernel<false, true, 0> : rx4096_kernel<false, false, 0>);
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
     if (err_stream) CUDA_TRY(ctx, cudaMemsetAsync(err_stream, 0, sizeof(int32_t) * B, ctx->stream));

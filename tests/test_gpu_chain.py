@@ -414,3 +414,45 @@ def test_fused_kernels_are_deterministic_across_launches(G):
         else:
             for a, b_ in zip(ref4, cur):
                 assert torch.equal(a, b_) or (a.is_floating_point() and torch.equal(torch.nan_to_num(a), torch.nan_to_num(b_)))
+
+
+def test_persistent_wraparound_against_oracle(G):
+    """B = 640 streams > 2 x 148 persistent CTAs: every CTA of tx4096 / channel_t5 / rx4096 walks at least two streams, so the
+    prefetch cursor's stream-to-stream hop (`pf_advance`) and the per-stream state resets are compared with the oracle --
+    TX samples, channel output with imported normals, channel estimate, decided bits and per-stream error counts, for all
+    640 streams (the oracle's vectorised scrambler forms are bit-identical to its loops, `test_oracle_kats`)."""
+    import torch
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(640)
+    B = 640
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    normals = rng.standard_normal((B, 2, p.stream_len)).astype(np.float32)
+    bd = ctx.bits(bits.ravel())
+    tx = ctx.tx_chain(lp, bd, B)
+    hd = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
+    rx = ctx.channel_t5(tx, snr_db=14.0, h_dev=hd, normals_dev=torch.from_numpy(normals).to(ctx.device))
+    eps_near = 1e-3
+    res = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd, near_eps=eps_near, want_err_per_stream=True)
+    ctx.sync()
+    tx_h = tx.cpu().numpy().reshape(B, -1)
+    rx_h = rx.cpu().numpy().reshape(B, -1)
+    H = res["H"].cpu().numpy()
+    got = ctx.host_bits(res["bits"], B * p.stream_bits).reshape(B, -1)
+    eps = res["err_per_stream"].cpu().numpy()
+    counts = res["counts"].cpu().numpy()
+    mism, ref_err = 0, 0
+    for b in range(B):
+        t, _, _ = OC.tx_chain(p, bits[b], fast=True)
+        assert rel_err(tx_h[b], t) < 2e-6, b
+        r = OC.channel_task5(p, t, 14.0, TAPS5, normals=normals[b].astype(np.float64))
+        assert rel_err(rx_h[b], r) < 2e-6, b
+        ref = OC.rx_chain_task5(p, r, bits[b], fast=True)
+        assert rel_err(H[b], ref["H"]) < 2e-5, b
+        assert eps[b] == int(np.sum(got[b] != bits[b])), b
+        mism += int(np.sum(got[b] != ref["bits"]))
+        ref_err += ref["errors"]
+    assert counts[1] == B * p.stream_bits and counts[0] == int(eps.sum())
+    assert mism <= 3 * p.bps * counts[2]
+    assert abs(int(counts[0]) - ref_err) <= mism
