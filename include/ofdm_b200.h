@@ -284,6 +284,12 @@ OFDM_API int ofdm_rx_chain_t4(ofdm_ctx*, const ofdm_link_params*, const void* rx
                               int freq_desync, int mp_desync, const uint32_t* tx_bits_dev, uint32_t* out_bits_dev,
                               int64_t* counts_dev, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev, double* tau_dev,
                               double* phase_dev, void* H_dev, double near_eps);
+/* Same, and fail_dev (optional, B int32) receives 1 for every stream whose guard-interval detector found fewer than two
+ * runs and fell back to TgPosition = 65 (`AutoCorrFunction.m:21-24`) -- the detector-failure count reported beside BER. */
+OFDM_API int ofdm_rx_chain_t4_ex(ofdm_ctx*, const ofdm_link_params*, const void* rx_dev, int64_t B, int time_desync,
+                                 int freq_desync, int mp_desync, const uint32_t* tx_bits_dev, uint32_t* out_bits_dev,
+                                 int64_t* counts_dev, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev, double* tau_dev,
+                                 double* phase_dev, void* H_dev, double near_eps, int32_t* fail_dev);
 
 #ifdef __cplusplus
 }

@@ -581,6 +581,13 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
 extern "C" int ofdm_rx_chain_t4(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, int time_desync, int freq_desync, int mp_desync,
                                 const uint32_t* tx_bits, uint32_t* out_bits, int64_t* counts, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev,
                                 double* tau_dev, double* phase_dev, void* H_dev, double near_eps) {
+    return ofdm_rx_chain_t4_ex(ctx, lp, rx, B, time_desync, freq_desync, mp_desync, tx_bits, out_bits, counts, tg_dev, fo_dev, ifo_dev, tau_dev, phase_dev,
+                               H_dev, near_eps, nullptr);
+}
+
+extern "C" int ofdm_rx_chain_t4_ex(ofdm_ctx* ctx, const ofdm_link_params* lp, const void* rx, int64_t B, int time_desync, int freq_desync, int mp_desync,
+                                   const uint32_t* tx_bits, uint32_t* out_bits, int64_t* counts, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev,
+                                   double* tau_dev, double* phase_dev, void* H_dev, double near_eps, int32_t* fail_dev) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, lp && rx && B >= 0, "bad argument");
     REQUIRE(ctx, ctx->precision == OFDM_PREC_F32, "the fused Task-4 chain is FP32 only (compose the per-function calls in FP64 mode)");
@@ -622,7 +629,7 @@ extern "C" int ofdm_rx_chain_t4(ofdm_ctx* ctx, const ofdm_link_params* lp, const
     if (!fo_dev) fo_dev = fo_s;
     if (!tg_dev) tg_dev = tg_s;
     int rc = OFDM_OK;
-    if (time_desync || freq_desync) rc = ofdm_cp_autocorr(ctx, rx, B, L, lp->Tg, lp->Nfft, nullptr, tg_dev, fo_dev, nullptr);
+    if (time_desync || freq_desync) rc = ofdm_cp_autocorr(ctx, rx, B, L, lp->Tg, lp->Nfft, nullptr, tg_dev, fo_dev, fail_dev);
     if (rc == OFDM_OK) {
         const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
         if (out_bits && (stream_bits % 32 != 0 || p.frame_bits % 32 != 0)) {

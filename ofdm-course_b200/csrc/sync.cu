@@ -20,7 +20,8 @@
 // One thread owns one group: it keeps the suffix sums in registers and leaves the prefix sums in shared memory.
 template <typename T, bool ALIGNED>
 __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out, int tile,
-                                                              cx<T>* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words) {
+                                                              cx<T>* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words,
+                                                              const int32_t* __restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NE = AC_THREADS * AC_G;                 // samples staged per block
     const int PADN = NE + NE / AC_G;                  // one pad word per group: group stride 17 -> conflict-free
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_kernel(const cx<T>* __res
     T* Qa = Qim + PADN;
     T* Qb = Qa + PADN;
     const int64_t b = blockIdx.x;
+    if (gate && gate[b] == 0) return;
     const int64_t n0 = (int64_t)blockIdx.y * tile;
     const cx<T>* r = rx + b * L;
     const int tid = threadIdx.x;
@@ -106,11 +108,13 @@ __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
 }
 template <bool ALIGNED>
 __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out, int tile,
-                                                                  float2* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words) {
+                                                                  float2* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words,
+                                                                  const int32_t* __restrict__ gate) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NE = AC_THREADS * AC_G;                 // samples staged per block
     float4* Q = (float4*)smem_raw;                    // NE + NE/16 entries
     const int64_t b = blockIdx.x;
+    if (gate && gate[b] == 0) return;                 // second (full-length) scan: only streams the prefix scan left unresolved
     const int64_t n0 = (int64_t)blockIdx.y * tile;
     const float2* r = rx + b * L;
     const int tid = threadIdx.x;
@@ -198,10 +202,11 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* 
 template <typename T>
 __global__ void autocorr_detect_kernel(const cx<T>* __restrict__ rx, int64_t B, int64_t L, int W, int Nfft, int64_t n_out,
                                        const uint32_t* __restrict__ flags, int64_t flag_words, int32_t* __restrict__ tg_pos,
-                                       double* __restrict__ freq_off, int32_t* __restrict__ fail) {
+                                       double* __restrict__ freq_off, int32_t* __restrict__ fail, const int32_t* __restrict__ gate) {
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
+    if (gate && gate[b] == 0) return;
     const uint32_t* fw = flags + b * flag_words;
     const int BIG = 0x7fffffff;
     // first flagged index
@@ -256,28 +261,41 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
     REQUIRE(ctx, n_out >= 65, "stream too short for AutoCorrFunction (needs L-W-Nfft >= 65)");
     REQUIRE(ctx, W <= 1536, "window wider than 1536 samples (the tile of 16*(126 - W/16) outputs per block must stay positive)");
     if (B == 0) return OFDM_OK;
-    const int64_t flag_words = (n_out + 31) / 32;
-    uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words);
-    REQUIRE(ctx, flags != nullptr, "scratch allocation failed");
     REQUIRE(ctx, W >= AC_G, "window narrower than 16 samples");
     // outputs per block: every output needs groups a .. a + W/16 + 1 staged; keep the group count even (32-bit flag words)
     const int tile = AC_G * ((AC_THREADS - (W >> 4) - 2) & ~1);
-    const int tiles = (int)cdiv64(n_out, tile);
-    DISPATCH_T(ctx, {
-        size_t smem = 4 * sizeof(T) * (size_t)(AC_THREADS * AC_G + AC_THREADS);
-        if constexpr (std::is_same<T, float>::value) {
-            auto k1 = (W & 15) ? autocorr_f32_kernel<false> : autocorr_f32_kernel<true>;
-            k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const float2*)rx, L, W, Nfft, n_out, tile, (float2*)autocorr, flags, flag_words);
-        } else {
-            auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
-            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_out, tile, (cx<T>*)autocorr, flags, flag_words);
-        }
-        ctx->launches++;
-        autocorr_detect_kernel<T><<<(unsigned)cdiv64(B * 32, 128), 128, 0, ctx->stream>>>((const cx<T>*)rx, B, L, W, Nfft, n_out, flags, flag_words,
-                                                                                            tg_pos, freq_off, fail);
-    });
-    LAUNCH_CHECK(ctx);
+    // When the AutoCorr vector itself is not wanted, TgPosition is decided by the first run of indices above the threshold
+    // and by the mere EXISTENCE of a second run (`AutoCorrFunction.m:15-20`), which normally starts one symbol later.  So the
+    // first three symbol lengths are scanned first; a stream whose prefix already holds "first run, gap, flagged index" has
+    // exactly the result of the full scan, every other stream (fail flag set) is re-scanned at full length by gated kernels.
+    const int64_t n_prefix = cdiv64(3 * (int64_t)(Nfft + W), tile) * tile;
+    const bool two_stage = autocorr == nullptr && n_prefix < n_out && !getenv("OFDM_B200_FULL_AUTOCORR");
+    const int64_t flag_words = (n_out + 31) / 32;
+    uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words + sizeof(int32_t) * B + 64);
+    REQUIRE(ctx, flags != nullptr, "scratch allocation failed");
+    int32_t* fail_s = (int32_t*)(flags + B * flag_words);
+    if (two_stage && !fail) fail = fail_s;
+    for (int stage = two_stage ? 0 : 1; stage < 2; ++stage) {
+        const int64_t n_scan = stage == 0 ? n_prefix : n_out;
+        const int64_t fw = (n_scan + 31) / 32;
+        const int tiles = (int)cdiv64(n_scan, tile);
+        const int32_t* gate = (two_stage && stage == 1) ? fail : nullptr;
+        DISPATCH_T(ctx, {
+            size_t smem = 4 * sizeof(T) * (size_t)(AC_THREADS * AC_G + AC_THREADS);
+            if constexpr (std::is_same<T, float>::value) {
+                auto k1 = (W & 15) ? autocorr_f32_kernel<false> : autocorr_f32_kernel<true>;
+                k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const float2*)rx, L, W, Nfft, n_scan, tile, (float2*)autocorr, flags, fw, gate);
+            } else {
+                auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
+                if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const cx<T>*)rx, L, W, Nfft, n_scan, tile, (cx<T>*)autocorr, flags, fw, gate);
+            }
+            ctx->launches++;
+            autocorr_detect_kernel<T><<<(unsigned)cdiv64(B * 32, 128), 128, 0, ctx->stream>>>((const cx<T>*)rx, B, L, W, Nfft, n_scan, flags, fw,
+                                                                                                tg_pos, freq_off, fail, gate);
+        });
+        LAUNCH_CHECK(ctx);
+    }
     return OFDM_OK;
 }
 

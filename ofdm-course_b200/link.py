@@ -526,11 +526,12 @@ class Context:
         tau = torch.zeros(B, dtype=torch.float64, device=dev)
         ph = torch.zeros(B, dtype=torch.float64, device=dev)
         H = self.empty_c(B, lp.N_carrier) if want_H else None
-        self._chk(self.lib.ofdm_rx_chain_t4(self.h, C.byref(lp), self.p(rx_dev), B, int(bool(time_desync)), int(bool(freq_desync)), int(bool(mp_desync)),
-                                            self.p(tx_bits_dev), self.p(out_bits), self.p(counts), self.p(tg), self.p(fo), self.p(ifo), self.p(tau),
-                                            self.p(ph), self.p(H), float(near_eps)))
+        fail = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._chk(self.lib.ofdm_rx_chain_t4_ex(self.h, C.byref(lp), self.p(rx_dev), B, int(bool(time_desync)), int(bool(freq_desync)), int(bool(mp_desync)),
+                                               self.p(tx_bits_dev), self.p(out_bits), self.p(counts), self.p(tg), self.p(fo), self.p(ifo), self.p(tau),
+                                               self.p(ph), self.p(H), float(near_eps), self.p(fail)))
         return {"bits": out_bits, "counts": counts, "TgPosition": tg, "FreqOffset": fo, "IFO": ifo, "tau": tau, "phase_shift": ph, "H": H,
-                "near": counts[2]}
+                "near": counts[2], "fail": fail}
 
     def rx_chain_t5_host(self, lp, rx_host, B, tx_bits_host=None, out_bits_host=None, H_host=None, chunk=2048, near_eps=0.0):
         """Host buffers in, host buffers out (torch CPU tensors, ideally pinned).  Returns counts (3 int64:

@@ -204,6 +204,47 @@ def test_autocorr_fallback_and_ifo_failure(G):
     assert int(fail[0]) == 1
 
 
+def test_autocorr_prefix_scan_equals_full_scan(G):
+    """When the AutoCorr vector is not requested the detector scans three symbol lengths first and re-scans only the
+    unresolved streams (sync.cu): same TgPosition / FreqOffset / fail flag as the full-length scan and as the oracle, over
+    random STO/CFO draws at several SNRs, a noise-only stream (fallback 65), a silent stream and a one-symbol burst."""
+    import os
+    rng = np.random.default_rng(21)
+    streams, tg_ref, fo_ref = [], [], []
+    p = OC.params_task4()
+    for i in range(24):
+        sto = int(rng.integers(0, 1153))
+        cfo = float(rng.integers(0, 31) + rng.random() - 0.5)
+        _, _, rx = _task4_rx(rng, sto, cfo, snr=[5, 12, 25, None][i % 4], taps=[[0, 1], [4, .6], [10, .3]] if i % 2 else None)
+        streams.append(rx)
+    streams.append(crandn(rng, p.stream_len))                                   # no run at all
+    streams.append(np.zeros(p.stream_len, dtype=complex))                       # all NaN
+    burst = np.zeros(p.stream_len, dtype=complex)
+    burst[400:400 + 1152] = streams[0][1152:2304]                               # a single symbol: one run only
+    streams.append(burst)
+    late = np.zeros(p.stream_len, dtype=complex)
+    late[20000:] = streams[1][:p.stream_len - 20000]                            # first run far beyond the prefix
+    streams.append(late)
+    for x in streams:
+        _, tg, fo = O.AutoCorrFunction(x, p.T_Guard, p.Nfft)
+        tg_ref.append(tg); fo_ref.append(fo)
+    ctx = G.default_context("f32")
+    xd = ctx.cplx(np.stack(streams))
+    _, tg2, fo2, fail2 = ctx.cp_autocorr(xd, p.T_Guard, p.Nfft)
+    os.environ["OFDM_B200_FULL_AUTOCORR"] = "1"
+    try:
+        _, tg1, fo1, fail1 = ctx.cp_autocorr(xd, p.T_Guard, p.Nfft)
+    finally:
+        del os.environ["OFDM_B200_FULL_AUTOCORR"]
+    assert np.array_equal(tg2.cpu().numpy(), tg1.cpu().numpy()) and np.array_equal(fail2.cpu().numpy(), fail1.cpu().numpy())
+    assert np.array_equal(fo2.cpu().numpy(), fo1.cpu().numpy(), equal_nan=True)
+    assert list(tg2.cpu().numpy()) == tg_ref
+    fo_ref = np.asarray(fo_ref)
+    ok = np.isfinite(fo_ref)
+    assert np.array_equal(np.isnan(fo2.cpu().numpy()), ~ok) and np.max(np.abs(fo2.cpu().numpy()[ok] - fo_ref[ok])) < 2e-5
+    assert list(fail2.cpu().numpy()[-4:-1]) == [1, 1, 1] and int(fail2[-1]) == 0
+
+
 @pytest.mark.parametrize("sto,cfo", [(37, 7.24), (900, 0.24), (0, 0.0)])
 def test_fine_sync(G, sto, cfo):
     rng = np.random.default_rng(15)

@@ -70,7 +70,10 @@ def main():
     cntf = res["f"]["counts"].cpu().numpy()
     out["M2_task4_sync_chain_fused"] = {"streams": B, "symbols": syms, "ms": ms, "symbols_per_s": syms / ms * 1e3, "algorithmic_B_per_symbol": 9548,
                                         "GBps_algorithmic": 9548 * syms / ms / 1e6, "frac_of_measured_hbm": 9548 * syms / ms / 1e6 / PEAK,
-                                        "ber": float(cntf[0]) / float(cntf[1]), "note": "autocorr (2 kernels) + one persistent fused kernel"}
+                                        "ber": float(cntf[0]) / float(cntf[1]),
+                                        "detector_failures": int(res["f"]["fail"].sum().item()),
+                                        "ifo_not_found": int((res["f"]["IFO"] < 0).sum().item()),
+                                        "note": "autocorr prefix scan (+ gated full-length re-scan) + one persistent fused kernel"}
     ms_ac = timed(lambda: ctx.cp_autocorr(rx, p.T_Guard, p.Nfft))
     out["M2_task4_sync_chain_fused"]["autocorr_ms"] = ms_ac
 
