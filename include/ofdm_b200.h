@@ -291,6 +291,43 @@ OFDM_API int ofdm_rx_chain_t4_ex(ofdm_ctx*, const ofdm_link_params*, const void*
                                  int64_t* counts_dev, int32_t* tg_dev, double* fo_dev, int32_t* ifo_dev, double* tau_dev,
                                  double* phase_dev, void* H_dev, double near_eps, int32_t* fail_dev);
 
+/* ---- Monte-Carlo BER-vs-SNR sweep (the script loops) ------------------------------------------ */
+/* Replaces the SNR loops `Task 3/Main_model_Task_3.m:192-268` / `Task 5/Main_model_Task_5.m:303-346` (chain
+ * OFDM_SWEEP_TASK5: TX chain -> Noise -> multipath -> M1 RX chain) and the impaired channel of
+ * `Task 4/Main_model_Task_4.m:95-110,252-264,277-366` swept over SNR (chain OFDM_SWEEP_TASK4: TX chain -> Noise ->
+ * add_STO -> add_CFO -> multipath -> M2 RX chain with AutoCorrFunction / remove_IFO / fine_sync / estimate_channel).
+ * Streams are numbered globally, g = snr_index * streams_per_point + j; payload bits, noise, STO and CFO draws are
+ * Philox streams keyed by (seed, g), so the integer counters are identical for every (rank, world, tile) split.
+ * One call processes the rank-th of `world` equal contiguous shares of the global stream range (ofdm_sweep_share)
+ * and ADDS into counts_dev: n_snr x 4 int64, row i = {bit errors, bits, symbols within near_eps of a decision
+ * boundary, guard-interval detector failures (Task-4 chain)}.  The caller sums the rows of all ranks -- the path's
+ * only collective, one int64 all-reduce.  Everything is enqueued on the context's stream. */
+#define OFDM_SWEEP_TASK5 0
+#define OFDM_SWEEP_TASK4 1
+typedef struct ofdm_sweep_params {
+    int32_t chain;               /* OFDM_SWEEP_TASK5 / OFDM_SWEEP_TASK4 */
+    int32_t n_snr;
+    const double* snr_db_host;   /* n_snr SNR points in dB */
+    int64_t streams_per_point;
+    int64_t tile_streams;        /* streams per work item; 0 = 2048 */
+    int32_t rank, world;         /* share of the global stream range this call processes */
+    uint64_t seed;
+    const double* taps_host;     /* n_taps x 2 doubles (delay, amplitude), row-major; n_taps = 0: no multipath */
+    int32_t n_taps;
+    double near_eps;             /* 0 = near-boundary counter off */
+    int32_t sto_max;             /* Task-4 chain: Time_Delay ~ U{0..sto_max} (`Main_model_Task_4.m:101`: Nfft + T_Guard) */
+    int32_t cfo_int_max;         /* Task-4 chain: Freq_Shift = U{0..cfo_int_max} + U(-0.5, 0.5) (`:108`: 30) */
+} ofdm_sweep_params;
+OFDM_API int ofdm_sweep_ber(ofdm_ctx*, const ofdm_link_params*, const ofdm_sweep_params*, int64_t* counts_dev);
+/* first / count of the contiguous share of `total_streams` that (rank, world) processes */
+OFDM_API int ofdm_sweep_share(int64_t total_streams, int rank, int world, int64_t* first, int64_t* count);
+/* The sweep's synthetic inputs, also usable on their own: payload words of streams first_stream_id .. +n_streams-1
+ * (n_streams x words_per_stream uint32), and per-stream STO / CFO draws (either output may be NULL). */
+OFDM_API int ofdm_payload_bits(ofdm_ctx*, uint32_t* bits_dev, int64_t n_streams, int64_t words_per_stream, uint64_t seed,
+                               int64_t first_stream_id);
+OFDM_API int ofdm_draw_sto_cfo(ofdm_ctx*, int64_t B, uint64_t seed, int64_t first_stream_id, int sto_max, int cfo_int_max,
+                               int32_t* nsto_dev, double* cfo_dev);
+
 #ifdef __cplusplus
 }
 #endif

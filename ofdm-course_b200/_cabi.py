@@ -24,6 +24,14 @@ class LinkParams(C.Structure):
                 ("reg0_host", pu8), ("scramble", C.c_int32)]
 
 
+class SweepParams(C.Structure):
+    """``ofdm_sweep_params`` of include/ofdm_b200.h."""
+    _fields_ = [("chain", C.c_int32), ("n_snr", C.c_int32), ("snr_db_host", pdbl), ("streams_per_point", C.c_int64),
+                ("tile_streams", C.c_int64), ("rank", C.c_int32), ("world", C.c_int32), ("seed", C.c_uint64),
+                ("taps_host", pdbl), ("n_taps", C.c_int32), ("near_eps", C.c_double), ("sto_max", C.c_int32),
+                ("cfo_int_max", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ofdm_b200.h
 SIGNATURES = {
     "ofdm_ctx_create": (i32, [C.POINTER(vp), i32, i32]),
@@ -83,6 +91,10 @@ SIGNATURES = {
     "ofdm_rx_chain_t5_host": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, i64]),
     "ofdm_rx_chain_t5_host_eps": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, i64, dbl]),
     "ofdm_rx_chain_t4": (i32, [vp, C.POINTER(LinkParams), vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl]),
+    "ofdm_sweep_ber": (i32, [vp, C.POINTER(LinkParams), C.POINTER(SweepParams), vp]),
+    "ofdm_sweep_share": (i32, [i64, i32, i32, C.POINTER(i64), C.POINTER(i64)]),
+    "ofdm_payload_bits": (i32, [vp, vp, i64, i64, u64, i64]),
+    "ofdm_draw_sto_cfo": (i32, [vp, i64, u64, i64, i32, i32, vp, vp]),
     "ofdm_rx_chain_t4_ex": (i32, [vp, C.POINTER(LinkParams), vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp]),
 }
 

@@ -21,14 +21,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ofdm_b200 as G  # noqa: E402
 from ofdm_b200 import sweep  # noqa: E402
-import oracle as O  # noqa: E402
-from oracle import chains as OC  # noqa: E402
+from ofdm_b200 import layouts  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--streams-per-point", type=int, default=8192)
-    ap.add_argument("--block", type=int, default=8192)
+    ap.add_argument("--tile", type=int, default=2048)
+    ap.add_argument("--chain", default="task5", choices=["task5", "task4"])
     ap.add_argument("--snr-step", type=float, default=0.5)
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -36,27 +36,34 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = G.Context(local, "f32")
-    p = OC.params_task5(comb=4)
-    lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers, p.pilotCarriers, p.pilotValues)
-    h, _ = O.get_MP_channel_resp([[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]], p.Nfft)
+    if a.chain == "task5":
+        lp, taps = layouts.task5_link(ctx, comb=4), layouts.TAPS_TASK5
+    else:
+        lp, taps = layouts.task4_link(ctx), layouts.TAPS_TASK4
     snrs = np.arange(0.0, 30.0 + 1e-9, a.snr_step)
-    # warm-up at the timed block size, so that the 4 GB signal buffers are already in the allocator's cache (a first cudaMalloc of
-    # that size costs tens of milliseconds -- a seventh of the whole sweep) and every kernel variant has been loaded
-    sweep.ber_sweep_task5(ctx, lp, snrs[:2 * world], min(a.block, a.streams_per_point), a.block, h, rank=rank, world=world)
+    # warm-up at the timed tile size, so that the signal buffers are already in the allocator's pool (a first cudaMalloc of
+    # that size costs tens of milliseconds) and every kernel variant has been loaded
+    sweep.ber_sweep(ctx, lp, snrs[:2], a.tile * world, taps, a.chain, rank=rank, world=world, tile=a.tile)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t0 = time.perf_counter()
     l0 = ctx.launches
-    res = sweep.ber_sweep_task5(ctx, lp, snrs, a.streams_per_point, a.block, h, rank=rank, world=world, sync_every_item=bool(os.environ.get("OFDM_SWEEP_SYNC")))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    acc = sweep.sweep_local(ctx, lp, snrs, a.streams_per_point, taps, a.chain, rank=rank, world=world, tile=a.tile)
+    if world > 1:
+        sweep.reduce_counts(acc)
+    e1.record()
     torch.cuda.synchronize()
-    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=ctx.device)
+    res = acc.cpu().numpy()
+    dt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=ctx.device)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     if rank == 0:
-        syms = len(snrs) * a.streams_per_point * p.N_symb
+        syms = len(snrs) * a.streams_per_point * lp.S
         ber = res[:, 0] / np.maximum(res[:, 1], 1)
-        print(json.dumps({"workload": "M5: full TX -> AWGN + 6-tap multipath -> RX BER sweep, SNR 0:%g:30, %d streams x 14 symbols per point" % (a.snr_step, a.streams_per_point),
+        print(json.dumps({"workload": "M5 (%s chain): full TX -> channel -> RX BER sweep, SNR 0:%g:30, %d streams x %d symbols per point" % (a.chain, a.snr_step, a.streams_per_point, lp.S),
+                          "counters_sha1": __import__("hashlib").sha1(res.tobytes()).hexdigest(), "detector_failures": int(res[:, 3].sum()),
                           "n_gpus": world, "seconds": float(dt.item()), "symbols": syms, "symbols_per_s": syms / float(dt.item()),
                           "kernels_this_rank": int(ctx.launches - l0), "bits_per_point": int(res[0, 1]),
                           "ber_at_snr": {str(float(s)): float(b) for s, b in zip(snrs[::10], ber[::10])},
