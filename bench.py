@@ -153,18 +153,71 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def numa_place(local_rank, world):
+    """Before any pinned allocation: split the visible cores evenly over the local ranks (so the copy-issuing threads of
+    different ranks do not share cores) and prefer the GPU's own NUMA node for this process's pages, when the container
+    lets us.  Returns what was done, for the record."""
+    info = {}
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                             capture_output=True, text=True, timeout=10).stdout.strip()
+        bdf = out.lower()
+        if bdf.startswith("00000000:"):
+            bdf = "0000:" + bdf.split(":", 1)[1]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        info["gpu_numa_node"] = node
+    except Exception:
+        node = -1
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        if node >= 0:
+            try:
+                def expand(txt):
+                    out = []
+                    for part in txt.strip().split(","):
+                        a, _, b = part.partition("-")
+                        out += list(range(int(a), int(b or a) + 1))
+                    return out
+                local = [c for c in expand(open(f"/sys/devices/system/node/node{node}/cpulist").read()) if c in cpus]
+                if len(local) >= 2:
+                    cpus = local
+                    info["cores_on_gpu_node"] = len(local)
+            except Exception:
+                pass
+        if world > 1 and len(cpus) >= 2 * world:
+            per = len(cpus) // world
+            mine = cpus[(local_rank % world) * per:(local_rank % world + 1) * per]
+            os.sched_setaffinity(0, mine)
+            info["cores"] = f"{mine[0]}-{mine[-1]}"
+    except Exception:
+        pass
+    if node >= 0:
+        try:   # set_mempolicy(MPOL_PREFERRED = 1, nodemask, maxnode): pinned buffers land next to the GPU
+            import ctypes
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))
+            info["mempolicy_preferred_node"] = node if rc == 0 else f"refused (errno {ctypes.get_errno()})"
+        except Exception:
+            pass
+    return info
+
+
 def run_gpu(args, rank, world, local_rank):
+    import hashlib
     import torch
     import torch.distributed as dist
+    numa = numa_place(local_rank, world)
     import ofdm_b200 as G
-    import oracle as O
-    from oracle import chains as OC
+    from ofdm_b200 import layouts, sweep
 
     torch.cuda.set_device(local_rank)
     ctx = G.Context(local_rank, "f32")
-    p = OC.params_task5(comb=4)
-    lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers,
-                         p.pilotCarriers, p.pilotValues)
+    lp = layouts.task5_link(ctx, comb=4)         # M1 shape: the package's own layout helpers (no oracle in this arm)
+
+    class _P:                                    # the handful of sizes the rest of this function reads
+        Nfft, T_Guard, N_carrier, N_symb, stream_bits = lp.Nfft, lp.Tg, lp.N_carrier, lp.S, lp.stream_bits
+    p = _P
     B = args.streams
     S = p.N_symb
     words = p.stream_bits // 32
@@ -174,7 +227,7 @@ def run_gpu(args, rank, world, local_rank):
     gen.manual_seed(1000 + rank)
     tx_bits = torch.randint(-2**31, 2**31 - 1, (B * words,), dtype=torch.int32, device=dev, generator=gen)
     rx = torch.empty((B, S, p.Nfft + p.T_Guard), dtype=torch.complex64, device=dev)
-    h_dev = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
+    h_dev = ctx.cplx(ctx.mp_channel_resp(TAPS5, p.Nfft)[0])
     chunk = min(B, 2048)
     for c0 in range(0, B, chunk):
         nb = min(chunk, B - c0)
@@ -263,6 +316,61 @@ def run_gpu(args, rank, world, local_rank):
     e2e_val = world * Be * S * e2e_steps / e2e_s
     h2d = Be * S * p.Nfft * 8 + tb_h.numel() * 4      # the host entry leaves the cyclic prefix on the host (strided H2D copy)
     d2h = ob_h.numel() * 4 + H_h.numel() * 8 + 24
+    # host-side ceiling of the same transfer: a plain pinned H2D copy of the step's input bytes, all ranks at once
+    stage = torch.empty(h2d // 8, dtype=torch.complex64, device=dev)
+    src = rx_h.reshape(-1)[:stage.numel()]
+    stage.copy_(src, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        stage.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    cp_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([cp_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cp_s = float(t.item())
+    h2d_ceiling_gbs = world * 3 * stage.numel() * 8 / cp_s / 1e9
+    del stage, rx_h, tb_h, ob_h, H_h
+
+    # ---- M5 (BASELINE config 5): the full TX -> channel -> RX BER-vs-SNR sweep, STRONG scaling (fixed total work), one
+    # ofdm_sweep_ber call per rank + the path's only collective (int64 all-reduce).  Reported beside the headline.
+    m5 = {}
+    del rx, out_bits, H
+    torch.cuda.empty_cache()
+    snrs = np.arange(0.0, 30.0 + 1e-9, 0.5)
+    for chain, spp, taps, A_sym in (("task5", args.m5_streams, layouts.TAPS_TASK5, 144713.0), ("task4", args.m5_streams_t4, layouts.TAPS_TASK4, None)):
+        if spp <= 0:
+            continue
+        lps = lp if chain == "task5" else layouts.task4_link(ctx)
+        sweep.ber_sweep(ctx, lps, snrs[:2], args.m5_tile * world, taps, chain, seed=7, rank=rank, world=world, tile=args.m5_tile)   # warm the pool
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches
+        e0.record()
+        acc = sweep.sweep_local(ctx, lps, snrs, spp, taps, chain, seed=7, rank=rank, world=world, tile=args.m5_tile, near_eps=args.near_eps)
+        if world > 1:
+            dist.all_reduce(acc)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        res = acc.cpu().numpy()
+        syms = len(snrs) * spp * lps.S
+        ber = res[:, 0] / np.maximum(res[:, 1], 1)
+        rec = {"workload": f"SNR 0:0.5:30 (61 points) x {spp} streams x {lps.S} symbols, {chain} chain, tile {args.m5_tile} streams",
+               "scaling": "strong", "symbols": int(syms), "ms": ms, "symbols_per_s": syms / ms * 1e3,
+               "kernels_this_rank": int(ctx.launches - l0), "counters_sha1": hashlib.sha1(res.tobytes()).hexdigest(),
+               "ber_at_0_10_20_30_dB": [float(ber[i]) for i in (0, 20, 40, 60)], "near_boundary": int(res[:, 2].sum()),
+               "detector_failures": int(res[:, 3].sum())}
+        if A_sym:
+            pk = load_peaks()[0]
+            rec["algorithmic_bytes_per_symbol"] = A_sym      # 36,864 TX write + 73,728 channel read+write + 34,121 RX
+            rec["hbm_frac_per_gpu"] = A_sym * syms / (ms * 1e-3) / 1e9 / world / pk
+        m5[chain] = rec
 
     if rank != 0:
         return
@@ -275,14 +383,18 @@ def run_gpu(args, rank, world, local_rank):
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": B, "symbols_per_step_per_gpu": syms_per_step,
-                   "input_bytes_per_gpu": int(rx.numel() * 8), "l2_policy": "inputs (33.8 GB at the default batch) larger than L2; no flush needed",
+                   "input_bytes_per_gpu": int(B * S * (p.Nfft + p.T_Guard) * 8), "l2_policy": "inputs (33.8 GB at the default batch) larger than L2; no flush needed",
                    "noise": "Philox4x32-10 keyed by global stream id", "e2e_streams": Be, "e2e_chunk_streams": args.e2e_chunk,
                    "ber": float(cnt[0]) / max(float(cnt[1]), 1.0),
                    "near_eps": args.near_eps, "near_boundary_symbols_per_step": int(cnt[2]) // max(args.steps, 1) // world,
                    "data_symbols_per_step": int(cnt[1]) // 4 // max(args.steps, 1) // world,
                    "ms_per_step_without_near_counter": near_off_ms},
         "clocks": sampler.summary(),
-        "e2e": {"value": e2e_val, "unit": "symbols/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e": {"value": e2e_val, "unit": "symbols/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "h2d_gbs": world * h2d * e2e_steps / e2e_s / 1e9, "plain_pinned_h2d_copy_gbs_all_ranks": h2d_ceiling_gbs,
+                "streams": Be, "why_not_headline_batch": "pinning 33.8 GB per rank takes longer than the measurement; the rate is set by the host link, not by the batch",
+                "numa": numa},
+        "m5": m5,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ((traffic or {}).get("dram_bytes_per_symbol") or 0) * syms_per_step or None, "peak_source": peak_src,
@@ -305,7 +417,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU per step (M1: 65,536 = 917,504 symbols)")
-    ap.add_argument("--e2e-streams", type=int, default=4096)
+    ap.add_argument("--e2e-streams", type=int, default=8192)
+    ap.add_argument("--m5-streams", type=int, default=8192, help="streams per SNR point of the Task-5 sweep record (0 = skip)")
+    ap.add_argument("--m5-streams-t4", type=int, default=2048, help="streams per SNR point of the Task-4 (STO/CFO) sweep record (0 = skip)")
+    ap.add_argument("--m5-tile", type=int, default=2048)
     ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--ref-streams", type=int, default=200, help="distinct streams per host process in the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="RX-chain time per host process in the CPU sample")
