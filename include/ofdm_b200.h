@@ -205,6 +205,13 @@ OFDM_API int ofdm_pilot_ls(ofdm_ctx*, const void* grid_dev, int64_t B, int S, in
 OFDM_API int ofdm_omp(ofdm_ctx*, const void* y_dev, int64_t B, int Np, const void* A_dev, int Ldict,
                       const int32_t* pilot_loc_host, int Nfft, int K, void* H_dev, void* h_dev,
                       int32_t* index_dev, int32_t* iters_dev);
+/* Same, and near_ties_dev (optional, B int32) receives per frame the number of iterations whose two largest |A^H r|^2
+ * differ by less than tie_eps (relative): the tap ORDER of such a frame may differ from a float64 evaluation.
+ * Partial-DFT dictionaries (the descriptor, or a dense matrix recognised as one) run as Batch-OMP -- one FFT per frame
+ * and the Toeplitz Gram vector; unstructured dense dictionaries in large batches run their correlations on tcgen05. */
+OFDM_API int ofdm_omp_ex(ofdm_ctx*, const void* y_dev, int64_t B, int Np, const void* A_dev, int Ldict,
+                         const int32_t* pilot_loc_host, int Nfft, int K, void* H_dev, void* h_dev,
+                         int32_t* index_dev, int32_t* iters_dev, int32_t* near_ties_dev, double tie_eps);
 OFDM_API int ofdm_mp(ofdm_ctx*, const void* y_dev, int64_t B, int Np, const void* A_dev, int Ldict,
                      const int32_t* pilot_loc_host, int Nfft, int K, void* H_dev, void* h_dev,
                      int32_t* index_dev);

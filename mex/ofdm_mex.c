@@ -31,7 +31,7 @@ static ofdm_ctx* g_ctx = NULL;
 static int g_prec = OFDM_PREC_F32;
 
 /* ---- scratch bookkeeping: everything allocated during one call is released on exit or error ---- */
-#define MAX_TMP 64
+#define MAX_TMP 96
 static void* g_dev[MAX_TMP]; static int g_ndev = 0;
 static void* g_host[MAX_TMP]; static int g_nhost = 0;
 static void release_all(void) {
@@ -181,6 +181,44 @@ static double* dev_doubles(const double* h, size_t n) {
 }
 static mxArray* scalar_from_dev_f64(const double* d) { double v; chk(ofdm_d2h(g_ctx, &v, d, 8), "d2h"); return mxCreateDoubleScalar(v); }
 static mxArray* scalar_from_dev_i32(const int32_t* d) { int32_t v; chk(ofdm_d2h(g_ctx, &v, d, 4), "d2h"); return mxCreateDoubleScalar((double)v); }
+
+
+/* ---- batched / fused ops: the link description travels as ten positional arguments --------------------------------
+ *   LINK = Nfft, T_Guard, N_carrier, N_symb, SpF, Constellation, dataCarriers, pilotCarriers, pilotValues, Register
+ * (the literals at the top of every reference script, `Task 5/Main_model_Task_5.m:6-46`); matlab/ofdm_link.m packs a
+ * struct into this list.  Batches are columns: one serial stream / one stream's bits per column. */
+#define N_LINK 10
+static void parse_link(const mxArray* const* a, ofdm_link_params* lp) {
+    int nd = 0, np = 0;
+    memset(lp, 0, sizeof *lp);
+    lp->Nfft = (int32_t)mxGetScalar(a[0]); lp->Tg = (int32_t)mxGetScalar(a[1]); lp->N_carrier = (int32_t)mxGetScalar(a[2]);
+    lp->S = (int32_t)mxGetScalar(a[3]); lp->SpF = (int32_t)mxGetScalar(a[4]);
+    lp->constellation = constellation_id(a[5]);
+    lp->data_carriers_host = to_i32(a[6], &nd);
+    lp->pilot_carriers_host = to_i32(a[7], &np);
+    lp->Nd = nd; lp->Np = np;
+    if (lp->S <= 0 || lp->SpF <= 0 || lp->S % lp->SpF) fail("ofdm:arg:link", "N_symb must be a positive multiple of SpF");
+    if (mxGetNumberOfElements(a[8]) == (size_t)np * lp->S) lp->pilot_vals_host = to_cdoubles(a[8], (size_t)np * lp->S);
+    else if (mxGetNumberOfElements(a[8]) == (size_t)np) {            /* one column: the same pilots in every symbol */
+        double* col = to_cdoubles(a[8], (size_t)np);
+        double* all = (double*)hostbuf((size_t)np * lp->S * 16);
+        int s2;
+        for (s2 = 0; s2 < lp->S; ++s2) memcpy(all + (size_t)s2 * np * 2, col, (size_t)np * 16);
+        lp->pilot_vals_host = all;
+    } else fail("ofdm:arg:pilots", "pilotValues must be Np x N_symb or Np x 1");
+    lp->reg0_host = to_reg(a[9]);
+    lp->scramble = 1;
+}
+static int64_t link_stream_bits(const ofdm_link_params* lp) { int bps = 0; ofdm_constellation(lp->constellation, NULL, &bps); return (int64_t)lp->S * lp->Nd * bps; }
+/* host matrix of 0/1 doubles, one stream per column (rows = stream_bits, a multiple of 32) -> packed words, host */
+static uint32_t* pack_bit_columns(const mxArray* a, size_t bits, size_t B) {
+    size_t words = bits / 32, b, i;
+    uint32_t* h = (uint32_t*)hostbuf(words * B * 4 + 4);
+    const double* p = real_data(a);
+    for (b = 0; b < B; ++b)
+        for (i = 0; i < bits; ++i) if (p[b * bits + i] != 0.0) h[b * words + (i >> 5)] |= 1u << (i & 31);
+    return h;
+}
 
 #define NEED(n) do { if (nrhs < (n) + 1) fail("ofdm:arg:count", "too few input arguments"); } while (0)
 #define A(i) prhs[(i) + 1]
@@ -483,6 +521,104 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         }
         OUT(0, ox);
         OUT(1, oc);
+    } else if (!strcmp(op, "tx_chain")) {                 /* Tx (L x B) = tx_chain(LINK..., bits (stream_bits x B)) */
+        NEED(N_LINK + 1);
+        ofdm_link_params lp;
+        parse_link(&A(0), &lp);
+        int64_t sb = link_stream_bits(&lp);
+        size_t B, L = (size_t)lp.S * (lp.Nfft + lp.Tg);
+        if (sb % 32 || mxGetM(A(N_LINK)) != (size_t)sb) fail("ofdm:tx_chain:bits", "bits must be stream_bits x B with stream_bits = N_symb*Nd*bps divisible by 32");
+        B = mxGetN(A(N_LINK));
+        uint32_t* hb = pack_bit_columns(A(N_LINK), (size_t)sb, B);
+        uint32_t* db = (uint32_t*)devbuf((size_t)sb / 8 * B + 4);
+        void* tx = devbuf(L * B * esz());
+        chk(ofdm_h2d(g_ctx, db, hb, (size_t)sb / 8 * B), "h2d");
+        chk(ofdm_tx_chain(g_ctx, &lp, db, (int64_t)B, tx), op);
+        OUT(0, from_dev_complex(tx, L, B));
+    } else if (!strcmp(op, "channel_t5")) {               /* Rx = channel_t5(Tx (L x B), SNR_dB (scalar | 1 x B | []), h (FIR | []), seed) */
+        NEED(4);
+        size_t L = mxGetM(A(0)), B = mxGetN(A(0)), ns = mxGetNumberOfElements(A(1)), D = mxGetNumberOfElements(A(2)), b;
+        double* snr = NULL;
+        if (ns) {
+            double* sh = (double*)hostbuf(B * 8);
+            if (ns != 1 && ns != B) fail("ofdm:channel_t5:snr", "SNR_dB must be a scalar, 1 x B or empty");
+            for (b = 0; b < B; ++b) sh[b] = real_data(A(1))[ns == 1 ? 0 : b];
+            snr = dev_doubles(sh, B);
+        }
+        void* rx = devbuf(L * B * esz());
+        chk(ofdm_channel_t5(g_ctx, to_dev_complex(A(0), L * B), (int64_t)B, (int64_t)L, snr, NULL, (uint64_t)mxGetScalar(A(3)), 0,
+                            D ? to_dev_complex(A(2), D) : NULL, (int)D, rx), op);
+        OUT(0, from_dev_complex(rx, L, B));
+    } else if (!strcmp(op, "rx_chain_t5")) {   /* [bits (stream_bits x B), H (N_carrier x B), counts (1 x 3)] = rx_chain_t5(LINK..., Rx (L x B), tx_bits | [], near_eps) */
+        NEED(N_LINK + 3);
+        ofdm_link_params lp;
+        parse_link(&A(0), &lp);
+        int64_t sb = link_stream_bits(&lp);
+        size_t L = (size_t)lp.S * (lp.Nfft + lp.Tg), B = mxGetN(A(N_LINK)), i, b, words = (size_t)sb / 32;
+        int has_tx = mxGetNumberOfElements(A(N_LINK + 1)) != 0;
+        if (sb % 32) fail("ofdm:rx_chain_t5:bits", "stream_bits must be divisible by 32");
+        if (mxGetM(A(N_LINK)) != L) fail("ofdm:rx_chain_t5:size", "Rx must be (N_symb*(Nfft+T_Guard)) x B");
+        if (has_tx && (mxGetM(A(N_LINK + 1)) != (size_t)sb || mxGetN(A(N_LINK + 1)) != B)) fail("ofdm:rx_chain_t5:bits", "tx_bits must be stream_bits x B");
+        /* host buffers in the context's type; the library chunks and overlaps H2D / kernel / D2H itself */
+        void* rxh = hostbuf(L * B * esz());
+        for (i = 0; i < L * B; ++i) {
+            double re, im; get_complex(A(N_LINK), i, &re, &im);
+            if (g_prec == OFDM_PREC_F64) { ((double*)rxh)[2 * i] = re; ((double*)rxh)[2 * i + 1] = im; }
+            else { ((float*)rxh)[2 * i] = (float)re; ((float*)rxh)[2 * i + 1] = (float)im; }
+        }
+        uint32_t* txh = has_tx ? pack_bit_columns(A(N_LINK + 1), (size_t)sb, B) : NULL;
+        uint32_t* obh = (uint32_t*)hostbuf(words * B * 4 + 4);
+        void* Hh = hostbuf((size_t)lp.N_carrier * B * esz());
+        int64_t cnt[3] = {0, 0, 0};
+        chk(ofdm_rx_chain_t5_host_eps(g_ctx, &lp, rxh, (int64_t)B, txh, obh, Hh, cnt, 0, mxGetScalar(A(N_LINK + 2))), op);
+        mxArray* ob = mxCreateDoubleMatrix((size_t)sb, B, mxREAL);
+        for (b = 0; b < B; ++b)
+            for (i = 0; i < (size_t)sb; ++i) real_data(ob)[b * (size_t)sb + i] = (double)((obh[b * words + (i >> 5)] >> (i & 31)) & 1u);
+        OUT(0, ob);
+        mxArray* Hm = mxCreateDoubleMatrix((size_t)lp.N_carrier, B, mxCOMPLEX);
+        for (i = 0; i < (size_t)lp.N_carrier * B; ++i) {
+            if (g_prec == OFDM_PREC_F64) set_complex(Hm, i, ((double*)Hh)[2 * i], ((double*)Hh)[2 * i + 1]);
+            else set_complex(Hm, i, ((float*)Hh)[2 * i], ((float*)Hh)[2 * i + 1]);
+        }
+        OUT(1, Hm);
+        mxArray* cm = mxCreateDoubleMatrix(1, 3, mxREAL);
+        for (i = 0; i < 3; ++i) real_data(cm)[i] = (double)cnt[i];
+        OUT(2, cm);
+    } else if (!strcmp(op, "sweep_ber")) {   /* counts (n_snr x 4) = sweep_ber(LINK..., snrs, streams_per_point, taps (K x 2 | []), chain, seed, near_eps) */
+        NEED(N_LINK + 6);
+        ofdm_link_params lp;
+        ofdm_sweep_params sp;
+        char chain[16];
+        parse_link(&A(0), &lp);
+        memset(&sp, 0, sizeof sp);
+        size_t n = mxGetNumberOfElements(A(N_LINK)), i;
+        int K = (int)mxGetM(A(N_LINK + 2));
+        if (!n) fail("ofdm:sweep_ber:snr", "need at least one SNR point");
+        if (mxGetString(A(N_LINK + 3), chain, sizeof chain)) fail("ofdm:sweep_ber:chain", "chain must be 'task5' or 'task4'");
+        sp.chain = !strcmp(chain, "task4") ? OFDM_SWEEP_TASK4 : OFDM_SWEEP_TASK5;
+        sp.n_snr = (int32_t)n;
+        sp.snr_db_host = real_data(A(N_LINK));
+        sp.streams_per_point = (int64_t)mxGetScalar(A(N_LINK + 1));
+        sp.rank = 0; sp.world = 1;
+        sp.seed = (uint64_t)mxGetScalar(A(N_LINK + 4));
+        sp.near_eps = mxGetScalar(A(N_LINK + 5));
+        sp.sto_max = lp.Nfft + lp.Tg; sp.cfo_int_max = 30;            /* `Main_model_Task_4.m:101,108` */
+        if (mxGetNumberOfElements(A(N_LINK + 2))) {
+            double* tp = real_data(A(N_LINK + 2));
+            double* taps = (double*)hostbuf((size_t)K * 16);
+            int k2;
+            if (mxGetN(A(N_LINK + 2)) != 2) fail("ofdm:sweep_ber:taps", "channel_taps must be K x 2 (delay, amplitude)");
+            for (k2 = 0; k2 < K; ++k2) { taps[2 * k2] = tp[k2]; taps[2 * k2 + 1] = tp[K + k2]; }
+            sp.taps_host = taps; sp.n_taps = K;
+        }
+        int64_t* cd = (int64_t*)devbuf(n * 32);
+        int64_t* ch = (int64_t*)hostbuf(n * 32);
+        chk(ofdm_memset(g_ctx, cd, 0, n * 32), "memset");
+        chk(ofdm_sweep_ber(g_ctx, &lp, &sp, cd), op);
+        chk(ofdm_d2h(g_ctx, ch, cd, n * 32), "d2h");
+        mxArray* cm = mxCreateDoubleMatrix(n, 4, mxREAL);
+        for (i = 0; i < n; ++i) { int j; for (j = 0; j < 4; ++j) real_data(cm)[(size_t)j * n + i] = (double)ch[4 * i + j]; }
+        OUT(0, cm);
     } else {
         fail("ofdm:arg:op", "unknown operation");
     }

@@ -77,6 +77,7 @@ SIGNATURES = {
     "ofdm_equalize": (i32, [vp, vp, i64, i32, i32, vp, i32, i32, vp]),
     "ofdm_pilot_ls": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, vp]),
     "ofdm_omp": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp, vp]),
+    "ofdm_omp_ex": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp, vp, vp, dbl]),
     "ofdm_mp": (i32, [vp, vp, i64, i32, vp, i32, pi32, i32, i32, vp, vp, vp]),
     "ofdm_ber_count": (i32, [vp, vp, vp, i64, vp]),
     "ofdm_mer": (i32, [vp, vp, i64, i32, vp]),

@@ -213,12 +213,14 @@ void* ctx_scratch(ofdm_ctx* ctx, size_t bytes) {
     return ctx->scratch;
 }
 
-const void* ctx_twiddles(ofdm_ctx* ctx, int N) {
-    uint64_t key = ((uint64_t)N << 1) | (uint64_t)ctx->precision;
+const void* ctx_twiddles(ofdm_ctx* ctx, int N) { return ctx_twiddles_prec(ctx, N, ctx->precision); }
+
+const void* ctx_twiddles_prec(ofdm_ctx* ctx, int N, int precision) {
+    uint64_t key = ((uint64_t)N << 1) | (uint64_t)precision;
     auto it = ctx->twiddle_cache.find(key);
     if (it != ctx->twiddle_cache.end()) return it->second;
     void* d = nullptr;
-    if (ctx->precision == OFDM_PREC_F64) {
+    if (precision == OFDM_PREC_F64) {
         std::vector<double2> t(N);
         for (int k = 0; k < N; ++k) { long double a = -2.0L * M_PIl * k / N; t[k] = make_double2((double)cosl(a), (double)sinl(a)); }
         if (cudaMalloc(&d, sizeof(double2) * N) != cudaSuccess) return nullptr;

@@ -206,6 +206,7 @@ void* ctx_blob(ofdm_ctx* ctx, const void* host, size_t bytes);           // cach
 cudaError_t ctx_upload(void* dev, const void* host, size_t bytes);       // pageable H2D, complete on return
 void* ctx_scratch(ofdm_ctx* ctx, size_t bytes);                          // grow-only scratch
 const void* ctx_twiddles(ofdm_ctx* ctx, int N);                          // W_N^k, k=0..N-1, ctx precision
+const void* ctx_twiddles_prec(ofdm_ctx* ctx, int N, int precision);      // same table in a given precision
 const InterpPlan* ctx_plan(ofdm_ctx* ctx, const int32_t* knots1, int n, int ext_to /*0=no ext*/,
                            const int32_t* queries1 /*NULL => 1..nq*/, int nq, int method);
 uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull);

@@ -17,7 +17,8 @@ template <typename T, bool DENSE, bool IS_OMP>
 __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __restrict__ Y, int Np, const cx<T>* __restrict__ At, int Ldict,
                                                              const int32_t* __restrict__ p0, int Nfft, int logN, const cx<T>* __restrict__ tw,
                                                              const T* __restrict__ norms2, int K, cx<T>* __restrict__ Hout, cx<T>* __restrict__ hout,
-                                                             int32_t* __restrict__ index_out, int32_t* __restrict__ iters_out) {
+                                                             int32_t* __restrict__ index_out, int32_t* __restrict__ iters_out,
+                                                             int32_t* __restrict__ near_out, T tie_eps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using C = cx<T>;
     __shared__ double red[32];
@@ -28,7 +29,7 @@ __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __rest
     __shared__ int ucol[PU_MAXK], umult[PU_MAXK];
     __shared__ double2 G[PU_MAXK][PU_MAXK], Lm[PU_MAXK][PU_MAXK], grhs[PU_MAXK], xu[PU_MAXK];
     __shared__ C xs[PU_MAXK];             // coefficient per selection (x(i1))
-    __shared__ int s_stop;
+    __shared__ int s_stop, s_near;
     C* r = (C*)smem_raw;                  // residual
     C* yv = r + Np;                       // measurement
     C* fa = yv + Np;                      // FFT buffers (DFT path only)
@@ -38,12 +39,12 @@ __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __rest
     const int Nmask = Nfft - 1;
     const int search = IS_OMP ? Ldict : min(Np, Ldict);   // `MP_estimate.m:3,10`: only the first Np columns
     for (int i = tid; i < Np; i += PU_THREADS) { C v = Y[b * Np + i]; r[i] = v; yv[i] = v; }
-    if (tid == 0) s_stop = 0;
+    if (tid == 0) { s_stop = 0; s_near = 0; }
     __syncthreads();
     int nsel = 0, nu = 0;
     for (int it = 0; it < K; ++it) {
         // ---- correlation + argmax
-        T best = (T)-CUDART_INF; int bi = 0x7fffffff;
+        T best = (T)-CUDART_INF, second = (T)-CUDART_INF; int bi = 0x7fffffff;
         if (DENSE) {
             for (int l = tid; l < search; l += PU_THREADS) {
                 T ar = 0, ai = 0;
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __rest
                     m = m / norms2[l];
                     for (int q = 0; q < nsel; ++q) if (sel[q] == l) m = (T)-100;
                 }
-                if (m > best) { best = m; bi = l; }
+                if (m > best) { second = best; best = m; bi = l; } else if (m > second) second = m;
             }
         } else {
             for (int i = tid; i < Nfft; i += PU_THREADS) fa[i] = mk<T>(0, 0);
@@ -67,11 +68,26 @@ __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __rest
                     m = m / (T)Np;                                // ||a||^2 = Np for unit-modulus columns
                     for (int q = 0; q < nsel; ++q) if (sel[q] == l) m = (T)-100;
                 }
-                if (m > best) { best = m; bi = l; }
+                if (m > best) { second = best; best = m; bi = l; } else if (m > second) second = m;
             }
         }
+        const T my_best = best; const int my_bi = bi;
         block_argmax(best, bi, sval, sidx);
         const int col = (bi == 0x7fffffff) ? 0 : bi;   // all-NaN correlation: MATLAB's max returns index 1
+        if (near_out && IS_OMP) {                      // runner-up over the block: near-tie count (top-2 margin below tie_eps, relative)
+            T sec = (my_bi == bi) ? second : my_best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { T ov = __shfl_xor_sync(0xffffffffu, sec, o); sec = ov > sec ? ov : sec; }
+            __syncthreads();
+            if ((tid & 31) == 0) sval[tid >> 5] = sec;
+            __syncthreads();
+            if (tid == 0) {
+                T s2 = sval[0];
+                for (int w = 1; w < PU_THREADS / 32; ++w) s2 = sval[w] > s2 ? sval[w] : s2;
+                if (!(best - s2 > tie_eps * best)) s_near += 1;
+            }
+            __syncthreads();
+        }
         // ---- bookkeeping of the selection (duplicates share one unknown: pinv's minimum-norm split)
         int slot = -1;
         for (int q = 0; q < nu; ++q) if (ucol[q] == col) slot = q;
@@ -157,6 +173,7 @@ __global__ void __launch_bounds__(PU_THREADS) pursuit_kernel(const cx<T>* __rest
         if (hb) for (int q = 0; q < nu; ++q) hb[ucol[q]] = hval[q];
         if (index_out) for (int q = 0; q < K; ++q) index_out[b * K + q] = q < nsel ? sel[q] + 1 : 0;
         if (iters_out) iters_out[b] = nsel;
+        if (near_out) near_out[b] = s_near;
     }
     __syncthreads();
     if (Hout) {
@@ -179,11 +196,11 @@ __global__ void dict_prepare_kernel(const cx<T>* __restrict__ A, int Np, int Ldi
 }
 
 int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, int Nfft, int K, void* H, void* h, int32_t* index, int32_t* iters,
-                bool* handled);
+                int32_t* near_ties, double tie_eps, bool* handled);
 
 template <bool IS_OMP>
 static int pursuit_common(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, const int32_t* loc, int Nfft, int K, void* H,
-                          void* h, int32_t* index, int32_t* iters) {
+                          void* h, int32_t* index, int32_t* iters, int32_t* near_ties = nullptr, double tie_eps = 0.0) {
     REQUIRE(ctx, y && B >= 0 && Np >= 1 && Ldict >= 1 && K >= 1 && K <= PU_MAXK, "bad argument (K must be 1..32)");
     REQUIRE(ctx, is_pow2(Nfft) && Nfft >= 8 && Nfft <= (ctx->precision == OFDM_PREC_F64 ? 4096 : 8192), "unsupported Nfft");
     REQUIRE(ctx, Ldict <= Nfft, "dictionary wider than Nfft (indices address an Nfft-long CIR)");
@@ -214,8 +231,8 @@ static int pursuit_common(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const
         // static shared (Gram + Cholesky factor, ~34 KB) plus dynamic can pass 48 KB: always opt in
         CUDA_TRY(ctx, cudaFuncSetAttribute(kd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64 * 1024)));
         CUDA_TRY(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 64 * 1024)));
-        if (A) kd<<<(unsigned)B, PU_THREADS, smem, ctx->stream>>>((const C*)y, Np, At, Ldict, nullptr, Nfft, ilog2(Nfft), (const C*)tw, norms, K, (C*)H, (C*)h, index, iters);
-        else kf<<<(unsigned)B, PU_THREADS, smem, ctx->stream>>>((const C*)y, Np, nullptr, Ldict, p0, Nfft, ilog2(Nfft), (const C*)tw, nullptr, K, (C*)H, (C*)h, index, iters);
+        if (A) kd<<<(unsigned)B, PU_THREADS, smem, ctx->stream>>>((const C*)y, Np, At, Ldict, nullptr, Nfft, ilog2(Nfft), (const C*)tw, norms, K, (C*)H, (C*)h, index, iters, near_ties, (T)tie_eps);
+        else kf<<<(unsigned)B, PU_THREADS, smem, ctx->stream>>>((const C*)y, Np, nullptr, Ldict, p0, Nfft, ilog2(Nfft), (const C*)tw, nullptr, K, (C*)H, (C*)h, index, iters, near_ties, (T)tie_eps);
         ctx->launches++;
         if (A) { cudaFreeAsync(At, ctx->stream); cudaFreeAsync(norms, ctx->stream); }
     });
@@ -224,15 +241,48 @@ static int pursuit_common(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const
     return OFDM_OK;
 }
 
+int ofdm_omp_dft(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const int32_t* p0_dev, int Ldict, int Nfft, int K, void* H, void* h, int32_t* index,
+                 int32_t* iters, int32_t* near_ties, double tie_eps, bool* handled);
+int ofdm_omp_probe_dft(ofdm_ctx* ctx, const void* A, int Np, int Ldict, int Nfft, int32_t** p0_out, bool* is_dft);
+
 extern "C" int ofdm_omp(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, const int32_t* loc, int Nfft, int K, void* H,
                         void* h, int32_t* index, int32_t* iters) {
+    return ofdm_omp_ex(ctx, y, B, Np, A, Ldict, loc, Nfft, K, H, h, index, iters, nullptr, 0.0);
+}
+
+extern "C" int ofdm_omp_ex(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, const int32_t* loc, int Nfft, int K, void* H,
+                           void* h, int32_t* index, int32_t* iters, int32_t* near_ties, double tie_eps) {
     if (!ctx) return OFDM_ERR_INVALID;
-    if (A && y && B > 0 && Np >= 1 && Ldict >= 1 && K >= 1 && K <= PU_MAXK && is_pow2(Nfft) && Nfft >= 8 && Nfft <= 8192 && Ldict <= Nfft) {
-        bool handled = false;   // large batches with a dense dictionary: correlation on tcgen05 tensor cores (sparse_tc.cu)
-        int rc = ofdm_omp_tc(ctx, y, B, Np, A, Ldict, Nfft, K, H, h, index, iters, &handled);
-        if (rc || handled) return rc;
+    const bool sane = y && B > 0 && Np >= 1 && Ldict >= 1 && K >= 1 && K <= PU_MAXK && is_pow2(Nfft) && Nfft >= 8 && Nfft <= 8192 && Ldict <= Nfft;
+    if (sane && ctx->precision == OFDM_PREC_F32) {
+        // (1) partial-DFT dictionaries -- given as the descriptor, or recognised in a dense matrix -- take the Batch-OMP kernel
+        //     (sparse_dft.cu): one FFT per frame instead of K dense correlations
+        bool handled = false;
+        if (!A && loc) {
+            std::vector<int32_t> v(Np);
+            for (int i = 0; i < Np; ++i) { REQUIRE(ctx, loc[i] >= 1 && loc[i] <= Nfft, "pilot index out of range"); v[i] = loc[i] - 1; }
+            const int32_t* p0 = (const int32_t*)ctx_blob(ctx, v.data(), sizeof(int32_t) * Np);
+            REQUIRE(ctx, p0 != nullptr, "device upload failed");
+            int rc = ofdm_omp_dft(ctx, y, B, Np, p0, Ldict, Nfft, K, H, h, index, iters, near_ties, tie_eps, &handled);
+            if (rc || handled) return rc;
+        } else if (A && B >= 64 && !getenv("OFDM_B200_NO_DFT_PROBE")) {
+            int32_t* p0 = nullptr;
+            bool is_dft = false;
+            int rc = ofdm_omp_probe_dft(ctx, A, Np, Ldict, Nfft, &p0, &is_dft);
+            if (rc) return rc;
+            if (is_dft) {
+                rc = ofdm_omp_dft(ctx, y, B, Np, p0, Ldict, Nfft, K, H, h, index, iters, near_ties, tie_eps, &handled);
+                cudaFreeAsync(p0, ctx->stream);
+                if (rc || handled) return rc;
+            }
+        }
+        // (2) unstructured dense dictionaries in large batches: correlation on tcgen05 tensor cores (sparse_tc.cu)
+        if (A) {
+            int rc = ofdm_omp_tc(ctx, y, B, Np, A, Ldict, Nfft, K, H, h, index, iters, near_ties, tie_eps, &handled);
+            if (rc || handled) return rc;
+        }
     }
-    return pursuit_common<true>(ctx, y, B, Np, A, Ldict, loc, Nfft, K, H, h, index, iters);
+    return pursuit_common<true>(ctx, y, B, Np, A, Ldict, loc, Nfft, K, H, h, index, iters, near_ties, tie_eps);
 }
 extern "C" int ofdm_mp(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, const int32_t* loc, int Nfft, int K, void* H,
                        void* h, int32_t* index) {

@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
                                                                  const int32_t* __restrict__ cand, const float* __restrict__ cand_score,
                                                                  float* __restrict__ Rt, int32_t* __restrict__ sel_g, int32_t* __restrict__ nsel_g,
                                                                  float2* __restrict__ xs_g, double2* __restrict__ G_g, double2* __restrict__ rhs_g, int K,
-                                                                 int32_t* __restrict__ fallbacks) {
+                                                                 int32_t* __restrict__ fallbacks, int32_t* __restrict__ near_out, float tie_eps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double shred[4 * 2 * (TS_MAXK + 2)];
     __shared__ float sval[32];
@@ -135,13 +135,14 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
             if (lane == 0) { sc_m[w] = (float)(ar * ar + ai * ai); sc_c[w] = clw; }
             __syncthreads();
             if (tid == 0) {
-                float best = -CUDART_INF_F; int bi = 0x7fffffff;
+                float best = -CUDART_INF_F, sec = -CUDART_INF_F; int bi = 0x7fffffff;
 #pragma unroll
                 for (int c = 0; c < TC_TOP; ++c) {
                     const float m = sc_m[c];
-                    if (m > best || (m == best && sc_c[c] < bi)) { best = m; bi = sc_c[c]; }
+                    if (m > best || (m == best && sc_c[c] < bi)) { sec = best; best = m; bi = sc_c[c]; } else if (m > sec) sec = m;
                 }
                 s_col = (bi == 0x7fffffff) ? 0 : bi;
+                if (near_out && !(best - sec > tie_eps * best)) near_out[f] += 1;     // top-2 margin of the exact scores below tie_eps
             }
         } else {                                        // TF32 ranking too close to call: exact search over every column
             if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1);
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_step_kernel(const float2* _
                 if (m > best) { best = m; bi = l; }
             }
             block_argmax(best, bi, sval, sidx);
-            if (tid == 0) s_col = (bi == 0x7fffffff) ? 0 : bi;
+            if (tid == 0) { s_col = (bi == 0x7fffffff) ? 0 : bi; if (near_out) near_out[f] += 1; }   // the screen itself could not separate them
         }
     }
     // ---- unique columns so far (duplicates share one unknown: pinv's minimum-norm split)
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TS_THREADS) omp_tc_finish_kernel(const int32_t
 
 // returns OFDM_OK and sets *handled when the tensor-core path ran
 int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, int Ldict, int Nfft, int K, void* H, void* h, int32_t* index, int32_t* iters,
-                bool* handled) {
+                int32_t* near_ties, double tie_eps, bool* handled) {
     *handled = false;
     if (ctx->precision != OFDM_PREC_F32 || !A || K > TS_MAXK) return OFDM_OK;
     if (getenv("OFDM_B200_NO_TC")) return OFDM_OK;
@@ -317,6 +318,7 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
     CUDA_TRY(ctx, cudaMallocAsync((void**)&rhs, sizeof(double2) * (size_t)B * K, st));
     fb = nsel + B;
     CUDA_TRY(ctx, cudaMemsetAsync(fb, 0, sizeof(int32_t), st));
+    if (near_ties) CUDA_TRY(ctx, cudaMemsetAsync(near_ties, 0, sizeof(int32_t) * (size_t)B, st));
     tc_dict_kernel<<<Lpad, 128, 0, st>>>((const float2*)A, Np, Ldict, K2, Bt);
     tc_init_kernel<<<(unsigned)Bpad, 128, 0, st>>>((const float2*)y, B, Np, K2, Rt, nsel);
     ctx->launches += 2;
@@ -330,7 +332,7 @@ int ofdm_omp_tc(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const void* A, 
         cudaFuncSetAttribute(omp_tc_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_step, 64 * 1024));
         for (int it = 0; it < K; ++it) {
             tc_corr_top_kernel<<<(unsigned)(Bpad / TC_BM), TC_THREADS, TC_SMEM_TOP_BYTES, st>>>(mapA, mapB, 2 * Lpad / TC_BN, K2, Ldict, cand, score);
-            omp_tc_step_kernel<<<(unsigned)B, TS_THREADS, smem_step, st>>>((const float2*)y, (const float2*)A, Np, Ldict, K2, it, cand, score, Rt, sel, nsel, xs, Gs, rhs, K, fb);
+            omp_tc_step_kernel<<<(unsigned)B, TS_THREADS, smem_step, st>>>((const float2*)y, (const float2*)A, Np, Ldict, K2, it, cand, score, Rt, sel, nsel, xs, Gs, rhs, K, fb, near_ties, (float)tie_eps);
             ctx->launches += 2;
         }
         omp_tc_finish_kernel<<<(unsigned)B, TS_THREADS, 0, st>>>(sel, nsel, xs, K, Nfft, (const float2*)tw, (float2*)H, (float2*)h, index, iters);

@@ -375,7 +375,7 @@ class Context:
         return y
 
     # ---------------------------------------------------------------- a22/a23
-    def _pursuit(self, omp, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None):
+    def _pursuit(self, omp, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None, tie_eps=None):
         B, Np = y_dev.shape
         if A_dev is not None:
             Ldict = A_dev.numel() // Np
@@ -385,13 +385,19 @@ class Context:
         keep, pp = _i32(pilot_loc) if pilot_loc is not None else (None, None)  # noqa: F841 (keeps the array alive)
         if omp:
             iters = torch.zeros(B, dtype=torch.int32, device=self.device)
+            if tie_eps is not None:
+                near = torch.zeros(B, dtype=torch.int32, device=self.device)
+                self._chk(self.lib.ofdm_omp_ex(self.h, self.p(y_dev), B, Np, self.p(A_dev), Ldict, pp, Nfft, K, self.p(H), self.p(h), self.p(idx), self.p(iters),
+                                               self.p(near), float(tie_eps)))
+                return H, h, idx, iters, near
             self._chk(self.lib.ofdm_omp(self.h, self.p(y_dev), B, Np, self.p(A_dev), Ldict, pp, Nfft, K, self.p(H), self.p(h), self.p(idx), self.p(iters)))
             return H, h, idx, iters
         self._chk(self.lib.ofdm_mp(self.h, self.p(y_dev), B, Np, self.p(A_dev), Ldict, pp, Nfft, K, self.p(H), self.p(h), self.p(idx)))
         return H, h, idx
 
-    def omp(self, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None):
-        return self._pursuit(True, y_dev, Nfft, K, A_dev, Ldict, pilot_loc)
+    def omp(self, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None, tie_eps=None):
+        """``tie_eps``: also return per-frame near-tie counts (iterations whose top-2 |A^H r|^2 margin is below tie_eps)."""
+        return self._pursuit(True, y_dev, Nfft, K, A_dev, Ldict, pilot_loc, tie_eps)
 
     def mp(self, y_dev, Nfft, K, A_dev=None, Ldict=None, pilot_loc=None):
         return self._pursuit(False, y_dev, Nfft, K, A_dev, Ldict, pilot_loc)

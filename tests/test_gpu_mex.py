@@ -188,3 +188,56 @@ def test_mex_sync_chain_and_errors(mex):
         mex.call("no_such_function", 1.0)
     with pytest.raises(RuntimeError, match="too few"):
         mex.call("LS_CE", Y)
+
+
+def _link_args(p):
+    """The ten positional LINK arguments of the batched gateway ops (what matlab/ofdm_link.m builds from the script's struct)."""
+    return [float(p.Nfft), float(p.T_Guard), float(p.N_carrier), float(p.N_symb), float(p.Amount_ODFM_SpF), p.Constellation,
+            p.dataCarriers.astype(float), p.pilotCarriers.astype(float), p.pilotValues, O.DEFAULT_REGISTER.astype(float)]
+
+
+def test_mex_batched_chain_ops_against_oracle(mex):
+    """tx_chain / channel_t5 / rx_chain_t5 through the gateway with B = 3 streams as columns (the batched form of the loop
+    `Task 5/Main_model_Task_5.m:303-346`), each stage compared with the oracle."""
+    TAPS5 = [[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]]
+    p = OC.params_task5(comb=4)
+    rng = np.random.default_rng(17)
+    B = 3
+    bits = rng.integers(0, 2, (p.stream_bits, B)).astype(float)            # one stream per column
+    link = _link_args(p)
+    tx = mex.call("tx_chain", *link, bits)
+    assert tx.shape == (p.stream_len, B)
+    refs = [OC.tx_chain(p, bits[:, b], fast=True)[0] for b in range(B)]
+    for b in range(B):
+        assert rel(tx[:, b], refs[b]) < 2e-6
+    h, _ = O.get_MP_channel_resp(TAPS5, p.Nfft)
+    clean = mex.call("channel_t5", tx, np.zeros((0, 0)), h, 0.0)            # no noise: pure multipath, comparable with the oracle
+    for b in range(B):
+        assert rel(clean[:, b], O.apply_channel(tx[:, b], h)) < 2e-6
+    rx = mex.call("channel_t5", tx, 18.0, h, 5.0)                          # Philox noise, seed 5
+    snr_meas = 10 * np.log10(np.mean(np.abs(tx) ** 2) / np.mean(np.abs(rx - clean) ** 2 / np.sum(np.abs(h) ** 2)))
+    assert abs(snr_meas - 18.0) < 0.2
+    out_bits, H, counts = mex.call("rx_chain_t5", *link, rx, bits, 1e-3, nout=3)
+    assert out_bits.shape == (p.stream_bits, B) and H.shape == (p.N_carrier, B) and counts.shape == (1, 3)
+    mism, ref_err = 0, 0
+    for b in range(B):
+        ref = OC.rx_chain_task5(p, rx[:, b], bits[:, b], fast=True)         # the oracle on the very samples the gateway returned
+        assert rel(H[:, b], ref["H"]) < 2e-5
+        mism += int(np.sum(out_bits[:, b] != ref["bits"]))
+        ref_err += ref["errors"]
+    assert counts[0, 1] == B * p.stream_bits and counts[0, 0] == np.sum(out_bits != bits)
+    assert mism <= 3 * p.bps * counts[0, 2] and abs(counts[0, 0] - ref_err) <= mism
+
+
+def test_mex_sweep_ber(mex):
+    """sweep_ber through the gateway == ofdm_sweep_ber through the ctypes binding (same seeds), both chains."""
+    import ofdm_b200 as G
+    from ofdm_b200 import sweep
+    ctx = G.default_context("f32")
+    for chain, p, taps, snrs, spp in (("task5", OC.params_task5(comb=4), [[0, 1], [4, .8], [10, .6], [15, .4], [21, .2], [25, .1]], [5.0, 15.0], 6),
+                                      ("task4", OC.params_task4(), [[0, 1], [4, .6], [10, .3]], [10.0, 30.0], 5)):
+        got = mex.call("sweep_ber", *_link_args(p), np.asarray(snrs), float(spp), np.asarray(taps, dtype=float), chain, 3.0, 1e-3)
+        lp = ctx.link_params(p.Nfft, p.T_Guard, p.N_carrier, p.N_symb, p.Amount_ODFM_SpF, p.Constellation, p.dataCarriers, p.pilotCarriers, p.pilotValues)
+        want = sweep.ber_sweep(ctx, lp, snrs, spp, taps, chain, seed=3, near_eps=1e-3)
+        assert got.shape == (len(snrs), 4) and np.array_equal(got.astype(np.int64), want)
+        assert np.all(got[:, 1] == spp * p.stream_bits) and got[0, 0] > got[1, 0]
