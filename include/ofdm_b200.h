@@ -184,6 +184,12 @@ OFDM_API int ofdm_ls_ce(ofdm_ctx*, const void* grid_dev, int64_t B, int S, int N
 OFDM_API int ofdm_mmse_ce(ofdm_ctx*, const void* grid_dev, int64_t B, int S, int Nfft,
                           const int32_t* pilot_loc_host, int Np, const double* pilot_vals_host,
                           int N_carrier, const void* h_dev, int h_len, const double* snr_db_dev, void* H_dev);
+/* MMSE_CE for a batch that shares its channel statistics (one Monte-Carlo point, `Task 5/Task5_part2.m:176-177`): ONE
+ * impulse response h_dev (h_len complex, gives tau_rms) and ONE SNR for all B streams.  W = I - Rpp^{-1}/snr is built once
+ * and applied to every stream as a complex matrix product on the tensor cores (TF32 two-term split, FP32 accuracy). */
+OFDM_API int ofdm_mmse_ce_shared(ofdm_ctx*, const void* grid_dev, int64_t B, int S, int Nfft,
+                                 const int32_t* pilot_loc_host, int Np, const double* pilot_vals_host,
+                                 int N_carrier, const void* h_dev, int h_len, double snr_db, void* H_dev);
 /* (`Task 5/interpolate.m:1-24`) Hp_dev: B x Np -> H_dev: B x N. */
 OFDM_API int ofdm_interpolate(ofdm_ctx*, const void* Hp_dev, int64_t B, const int32_t* pilot_loc_host, int Np,
                               int N, int method, void* H_dev);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "ofdm_estimate_channel": (i32, [vp, vp, i64, i32, i32, pi32, i32, pi32, i32, pdbl, vp, vp]),
     "ofdm_ls_ce": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, i32, vp]),
     "ofdm_mmse_ce": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, i32, vp, i32, vp, vp]),
+    "ofdm_mmse_ce_shared": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, i32, vp, i32, dbl, vp]),
     "ofdm_interpolate": (i32, [vp, vp, i64, pi32, i32, i32, i32, vp]),
     "ofdm_equalize": (i32, [vp, vp, i64, i32, i32, vp, i32, i32, vp]),
     "ofdm_pilot_ls": (i32, [vp, vp, i64, i32, i32, pi32, i32, pdbl, vp]),

@@ -68,9 +68,19 @@ __device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
     return r;
 }
 
-// NG = groups of 256 dictionary columns a thread works on (Ldict <= 256 NG)
+// NG = groups of 256 dictionary columns a thread works on (Ldict <= 256 NG).
+//
+// The re-fit is carried in ORTHOGONALISED form, so that an iteration needs no triangular solve and the correlation is
+// updated in place (only the running alpha lives in registers):
+//   u_n = a_{c_n} - sum_{j<n} gamma_jn u_j  = sum_{i<=n} T_in a_{c_i}        (Gram-Schmidt on the selected columns)
+//   gamma_jn = u_j^H a_{c_n} / ||u_j||^2 = sum_{i<=j} conj(T_ij) G[c_i][c_n] / ||u_j||^2,   G[c_i][c_n] = g[(c_i - c_n) mod N]
+//   beta_n = u_n^H y / ||u_n||^2 = sum_{i<=n} conj(T_in) b_i / ||u_n||^2,     b_i = conj(a_{c_i}) . y
+//   r_n = r_{n-1} - u_n beta_n   =>   alpha_n[l] = alpha_{n-1}[l] - sum_{i<=n} (beta_n T_in) g[(l - c_i) mod N]
+//   ||r_n - r_{n-1}|| = |beta_n| ||u_n||,  ||r_n||^2 = ||r_{n-1}||^2 - |beta_n|^2 ||u_n||^2      (the stopping rule, :20)
+//   x = T beta  is exactly pinv(A_sel) * y  (`OMP_estimate.m:9,17`), formed once at the end.
+// All of that is O(k) per lane and iteration, in double; the k+1 coefficients beta_n T_in go to the FP32 update.
 template <int NG>
-__global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __restrict__ Y, int Np, const int32_t* __restrict__ p0, int Ldict, int Nfft,
+__global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __restrict__ Y, int Np, const int32_t* __restrict__ p0, int Ldict, int Nfft,
                                                                 int logN, const float2* __restrict__ tw, const double2* __restrict__ tw_d,
                                                                 const float2* __restrict__ g_f, const double2* __restrict__ g_d, int K,
                                                                 float2* __restrict__ Hout, float2* __restrict__ hout, int32_t* __restrict__ index_out,
@@ -78,11 +88,13 @@ __global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[2 * (OD_THREADS / 32)];
     __shared__ Top2 stop2[OD_THREADS / 32];
-    __shared__ int sel[OD_MAXK], uniq[OD_MAXK], ucol[OD_MAXK], umult[OD_MAXK];
-    __shared__ double2 G[OD_MAXK][OD_MAXK], Lm[OD_MAXK][OD_MAXK], grhs[OD_MAXK], zf[OD_MAXK], xu[OD_MAXK], xprev[OD_MAXK];
-    __shared__ double linv[OD_MAXK];
-    __shared__ float2 xuf[OD_MAXK], xs[OD_MAXK];
+    __shared__ int sel[OD_MAXK], ucol[OD_MAXK];
+    __shared__ double2 Tm[OD_MAXK][OD_MAXK + 1];      // T[i][n], i <= n
+    __shared__ double2 bvec[OD_MAXK], beta[OD_MAXK];
+    __shared__ double un2[OD_MAXK];                    // ||u_j||^2
+    __shared__ float2 wf[OD_MAXK], xs[OD_MAXK];
     __shared__ int s_nu, s_nsel, s_stop, s_near, s_col, s_new;
+    __shared__ double s_rr;                            // ||r_{n-1}||^2
     float2* fa = (float2*)smem_raw;
     float2* fb = fa + Nfft;
     const int64_t f = blockIdx.x;
@@ -97,11 +109,12 @@ __global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __
     for (int i = tid; i < Np; i += OD_THREADS) { const float2 v = y[i]; fa[p0[i]] = v; yy += (double)v.x * v.x + (double)v.y * v.y; }
     if (tid == 0) { s_nu = 0; s_nsel = 0; s_stop = 0; s_near = 0; }
     yy = block_sum(yy, red);          // (barriers inside: the scatter is complete)
+    if (tid == 0) s_rr = yy;
     __syncthreads();
     float2* c = block_fft<float, true>(fa, fb, Nfft, logN, tw);
-    float2 a0[NG];
+    float2 a[NG];                     // the running correlation A^H r
 #pragma unroll
-    for (int j = 0; j < NG; ++j) { const int l = tid + OD_THREADS * j; a0[j] = l < Ldict ? c[l] : make_float2(0.f, 0.f); }
+    for (int j = 0; j < NG; ++j) { const int l = tid + OD_THREADS * j; a[j] = l < Ldict ? c[l] : make_float2(0.f, 0.f); }
     __syncthreads();
     // g twice in a row (both FFT buffers are free now): entry (l - c) mod Nfft is read as gS[base + 256 j] with ONE base per
     // selected tap and immediate offsets, no wrap-around arithmetic in the inner loop
@@ -111,21 +124,7 @@ __global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __
 
     for (int it = 0; it < K; ++it) {
         const int nu = s_nu, nsel = s_nsel;
-        // ---- correlation with the residual through the Toeplitz Gram vector (`OMP_estimate.m:7,14`)
-        float2 a[NG];
-#pragma unroll
-        for (int j = 0; j < NG; ++j) a[j] = a0[j];
-        for (int q = 0; q < nu; ++q) {
-            const float2 x = xuf[q];
-            const float2* gp = gS + ((tid - ucol[q]) & Nmask);
-#pragma unroll
-            for (int j = 0; j < NG; ++j) {
-                const float2 gv = gp[OD_THREADS * j];
-                a[j].x = fmaf(-x.x, gv.x, fmaf(x.y, gv.y, a[j].x));
-                a[j].y = fmaf(-x.x, gv.y, fmaf(-x.y, gv.x, a[j].y));
-            }
-        }
-        // ---- first maximum of |.|^2 and the runner-up, one fused block reduction
+        // ---- first maximum of |A^H r|^2 and the runner-up, one fused block reduction (`OMP_estimate.m:7,14`)
         Top2 t; t.b1 = -CUDART_INF_F; t.i1 = 0x7fffffff; t.b2 = -CUDART_INF_F;
 #pragma unroll
         for (int j = 0; j < NG; ++j) {
@@ -152,23 +151,22 @@ __global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __
             if (lane == 0) {
                 const int col = (t.i1 == 0x7fffffff) ? 0 : t.i1;          // all-NaN correlation: MATLAB's max returns index 1
                 if (!(t.b1 - t.b2 > tie_eps * t.b1)) s_near += 1;
-                // selection bookkeeping (duplicates share one unknown: pinv's minimum-norm split)
                 int slot = -1;
                 for (int q = 0; q < nu; ++q) if (ucol[q] == col) slot = q;
                 sel[nsel] = col;
-                if (slot < 0) { ucol[nu] = col; umult[nu] = 1; uniq[nsel] = nu; s_new = 1; s_nu = nu + 1; }
-                else { umult[slot] += 1; uniq[nsel] = slot; s_new = 0; }
+                if (slot < 0) { ucol[nu] = col; s_new = 1; s_nu = nu + 1; } else s_new = 0;
                 s_nsel = nsel + 1;
                 s_col = col;
             }
         }
         __syncthreads();
-        const int col = s_col, is_new = s_new, nsel2 = nsel + 1;
-        if (is_new) {
-            // right-hand side conj(a_new) * y in double: one table twiddle per pilot, block-wide
+        const int col = s_col, is_new = s_new;
+        if (!is_new) break;               // a column selected twice leaves the residual unchanged: ||r_i - r_{i-1}|| = 0 < 1e-2 (`:20`), it >= 1 always here
+        {
+            // b_n = conj(a_new) . y in double: one table twiddle per pilot, block-wide
             double ar = 0, ai = 0;
             for (int i = tid; i < Np; i += OD_THREADS) {
-                const double2 w = tw_d[(p0[i] * col) & Nmask];             // exp(-2*pi*1j*p*col/N); its conjugate is conj(A(i,col))... A = w
+                const double2 w = tw_d[(p0[i] * col) & Nmask];             // A(i, col)
                 const float2 v = y[i];
                 ar += w.x * v.x + w.y * v.y; ai += w.x * v.y - w.y * v.x;  // conj(w) * v
             }
@@ -177,81 +175,78 @@ __global__ void __launch_bounds__(OD_THREADS, 2) omp_dft_kernel(const float2* __
             __syncthreads();
         }
         if (warp == 0) {
-            if (is_new) {
-                const int n = nu;                                          // index of the new unique column
-                if (lane == 0) {
-                    double sr = 0, si = 0;
-                    for (int w = 0; w < OD_THREADS / 32; ++w) { sr += red[2 * w]; si += red[2 * w + 1]; }
-                    grhs[n] = make_double2(sr, si);
-                }
-                for (int q = lane; q < n; q += 32) { const double2 gv = g_d[(ucol[q] - col) & Nmask]; G[q][n] = gv; G[n][q] = cconj(gv); }   // conj(a_q) * a_new
-                if (lane == 0) G[n][n] = g_d[0];
-                for (int q = lane; q < n; q += 32) xprev[q] = xu[q];
-                if (lane == 0) xprev[n] = make_double2(0, 0);
-                __syncwarp();
-                // the Cholesky factor grows by ONE row: l = L[n][0..n-1] solves sum_{r<=q} l_r conj(L[q][r]) = G[n][q]
-                // (right-looking forward substitution, lane q owns unknown q), then the diagonal
-                double2 acc = lane < n ? G[n][lane] : make_double2(0, 0);
-                double nrm = 0;
-                for (int r = 0; r < n; ++r) {
-                    const double2 mine = cscale(acc, linv[r]);
-                    const double2 lr = make_double2(__shfl_sync(0xffffffffu, mine.x, r), __shfl_sync(0xffffffffu, mine.y, r));
-                    if (lane == r) Lm[n][r] = lr;
-                    else if (lane > r && lane < n) acc = acc - cmul(lr, cconj(Lm[lane][r]));
-                    nrm += lr.x * lr.x + lr.y * lr.y;
-                }
-                const double dn2 = G[n][n].x - nrm;
-                const double dn_ = sqrt(fmax(dn2, 0.0));
-                if (lane == 0) { Lm[n][n] = make_double2(dn_, 0.0); linv[n] = dn_ > 0 ? 1.0 / dn_ : 0.0; }
-                __syncwarp();
-                // forward solve L z = b also grows by one entry: z_n = (b_n - sum_{r<n} L[n][r] z_r) / L[n][n]
-                {
-                    double2 part = lane < n ? cmul(Lm[n][lane], zf[lane]) : make_double2(0, 0);
-                    part.x = warp_sum(part.x); part.y = warp_sum(part.y);
-                    if (lane == 0) zf[n] = cscale(grhs[n] - part, linv[n]);
-                }
-                __syncwarp();
-                // back substitution L^H x = z over the n + 1 unknowns (right-looking)
-                const int k = n + 1;
-                double2 xa = lane < k ? zf[lane] : make_double2(0, 0);
-                for (int i = k - 1; i >= 0; --i) {
-                    const double2 mine = cscale(xa, linv[i]);
-                    const double2 xi = make_double2(__shfl_sync(0xffffffffu, mine.x, i), __shfl_sync(0xffffffffu, mine.y, i));
-                    if (lane == i) xa = xi;
-                    else if (lane < i) xa = xa - cmul(cconj(Lm[i][lane]), xi);
-                }
-                if (lane < k) { xu[lane] = xa; xuf[lane] = make_float2((float)xa.x, (float)xa.y); }
-                __syncwarp();
+            const int n = nu;                                              // index of the new column
+            double2 bn = make_double2(0, 0);
+            for (int w = 0; w < OD_THREADS / 32; ++w) { bn.x += red[2 * w]; bn.y += red[2 * w + 1]; }
+            if (lane == 0) bvec[n] = bn;
+            // gamma_j (lane j < n) = sum_{i<=j} conj(T_ij) G[c_i][c_n] / ||u_j||^2
+            const double2 gcol = lane < n ? g_d[(ucol[lane] - col) & Nmask] : make_double2(0, 0);     // G[c_lane][c_n]
+            double2 gam = make_double2(0, 0);
+            for (int i = 0; i < n; ++i) {
+                const double2 gi = make_double2(__shfl_sync(0xffffffffu, gcol.x, i), __shfl_sync(0xffffffffu, gcol.y, i));
+                if (lane < n && i <= lane) gam = gam + cmul(cconj(Tm[i][lane]), gi);
             }
-            const int nu2 = nu + is_new;
-            if (lane < nsel2) { const double2 v = cscale(xu[uniq[lane]], 1.0 / (double)umult[uniq[lane]]); xs[lane] = make_float2((float)v.x, (float)v.y); }
-            // stopping rule from the Gram quantities: r = y - A_U x  =>  ||r_i - r_{i-1}||^2 = d^H G d, d = x_i - x_{i-1};
-            // ||r_{i-1}||^2 = ||y||^2 - 2 Re(x^H b) + x^H G x   (`OMP_estimate.m:20`); a repeated column leaves r unchanged
-            if (it >= 1) {
-                double dn = 0, on = 0;
-                if (is_new && lane < nu2) {
-                    double2 gd = make_double2(0, 0), gx = make_double2(0, 0);
-                    for (int q = 0; q < nu2; ++q) { const double2 gq = G[lane][q]; gd = gd + cmul(gq, xu[q] - xprev[q]); gx = gx + cmul(gq, xprev[q]); }
-                    const double2 dl = xu[lane] - xprev[lane], xl = xprev[lane];
-                    dn = dl.x * gd.x + dl.y * gd.y;                                   // Re(conj(d_l) * (G d)_l)
-                    on = (xl.x * gx.x + xl.y * gx.y) - 2.0 * (xl.x * grhs[lane].x + xl.y * grhs[lane].y);
-                }
-                dn = warp_sum(dn); on = warp_sum(on) + yy;
-                if (lane == 0 && (!is_new || sqrt(fmax(dn, 0.0)) / sqrt(fmax(on, 0.0)) < 1e-2)) s_stop = 1;
+            const double u2 = lane < n ? un2[lane] : 1.0;
+            gam = (lane < n && u2 > 0) ? cscale(gam, 1.0 / u2) : make_double2(0, 0);
+            // ||u_n||^2 = G_nn - sum_j |gamma_j|^2 ||u_j||^2
+            double nn = lane < n ? (gam.x * gam.x + gam.y * gam.y) * u2 : 0.0;
+            nn = warp_sum(nn);
+            const double un = fmax(g_d[0].x - nn, 0.0);
+            // T_in (lane i < n) = - sum_{j=i}^{n-1} gamma_j T_ij ; T_nn = 1
+            double2 tin = make_double2(0, 0);
+            for (int j = 0; j < n; ++j) {
+                const double2 gj = make_double2(__shfl_sync(0xffffffffu, gam.x, j), __shfl_sync(0xffffffffu, gam.y, j));
+                if (lane < n && j >= lane) tin = tin - cmul(gj, Tm[lane][j]);
+            }
+            if (lane == n) tin = make_double2(1, 0);
+            if (lane <= n) Tm[lane][n] = tin;
+            // beta_n = sum_{i<=n} conj(T_in) b_i / ||u_n||^2
+            double2 part = make_double2(0, 0);
+            if (lane < n) part = cmul(cconj(tin), bvec[lane]);
+            else if (lane == n) part = bn;
+            part.x = warp_sum(part.x); part.y = warp_sum(part.y);
+            const double2 bt = un > 0 ? cscale(part, 1.0 / un) : make_double2(0, 0);
+            if (lane == 0) { un2[n] = un; beta[n] = bt; }
+            if (lane <= n) { const double2 w = cmul(bt, tin); wf[lane] = make_float2((float)w.x, (float)w.y); }
+            // stopping rule: ||r_n - r_{n-1}|| / ||r_{n-1}|| < 1e-2 from the second selection on
+            if (lane == 0) {
+                const double dn = (bt.x * bt.x + bt.y * bt.y) * un, on = s_rr;
+                if (it >= 1 && sqrt(fmax(dn, 0.0)) / sqrt(fmax(on, 0.0)) < 1e-2) s_stop = 1;
+                s_rr = on - dn;
             }
         }
         __syncthreads();
-        if (s_stop) break;
+        if (s_stop || it == K - 1) break;
+        // ---- alpha -= sum_{i<=n} (beta_n T_in) g[(l - c_i) mod N]
+        for (int q = 0; q <= nu; ++q) {
+            const float2 x = wf[q];
+            const float2* gp = gS + ((tid - ucol[q]) & Nmask);
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const float2 gv = gp[OD_THREADS * j];
+                a[j].x = fmaf(-x.x, gv.x, fmaf(x.y, gv.y, a[j].x));
+                a[j].y = fmaf(-x.x, gv.y, fmaf(-x.y, gv.x, a[j].y));
+            }
+        }
     }
     __syncthreads();
-    // ---- outputs: h(index(i1)) = x(i1) in selection order (later duplicates overwrite), H = fft(h) as a sum over the taps
+    // ---- gains x = T beta on the unique columns; a repeated last column shares its unknown (pinv's minimum-norm split)
     const int nsel = s_nsel, nu = s_nu;
     __shared__ float2 hval[OD_MAXK];
-    if (tid == 0) {
-        for (int q = 0; q < nsel; ++q) hval[uniq[q]] = xs[q];
-        if (index_out) for (int q = 0; q < K; ++q) index_out[f * K + q] = q < nsel ? sel[q] + 1 : 0;
-        if (iters_out) iters_out[f] = nsel;
-        if (near_out) near_out[f] = s_near;
+    if (warp == 0) {
+        double2 xv = make_double2(0, 0);
+        if (lane < nu) for (int n = lane; n < nu; ++n) xv = xv + cmul(Tm[lane][n], beta[n]);
+        const int last = sel[nsel - 1];
+        const bool dup = nsel > nu;                      // the last selection repeated column `last`
+        if (lane < nu) {
+            hval[lane] = (dup && ucol[lane] == last) ? make_float2((float)(0.5 * xv.x), (float)(0.5 * xv.y)) : make_float2((float)xv.x, (float)xv.y);
+        }
+        __syncwarp();
+        if (lane == 0) {
+            if (index_out) for (int q = 0; q < K; ++q) index_out[f * K + q] = q < nsel ? sel[q] + 1 : 0;
+            if (iters_out) iters_out[f] = nsel;
+            if (near_out) near_out[f] = s_near;
+        }
     }
     __syncthreads();
     if (hout) {

@@ -31,11 +31,12 @@ static inline tc_encode_fn tc_get_encode() {
     return fn;
 }
 // rows x K FP32 matrix, K contiguous; box = 128 rows x 32 floats (128 B), 128B swizzle
-static inline bool tc_make_kmajor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t K) {
+// `ld` (elements, 0 = K): row pitch when the K extent addressed is a slice of wider rows
+static inline bool tc_make_kmajor_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t K, uint64_t ld = 0) {
     tc_encode_fn enc = tc_get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {K, rows};
-    cuuint64_t strides[1] = {K * sizeof(float)};
+    cuuint64_t strides[1] = {(ld ? ld : K) * sizeof(float)};
     cuuint32_t box[2] = {TC_BK, 128};
     cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -144,13 +145,14 @@ __device__ __forceinline__ void tc_mainloop(TcShared* sh, unsigned char* tiles, 
 }
 
 // Bring-up kernel: one tile per CTA, accumulator written to global memory.
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_store_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                                                                   float* __restrict__ D, int ldd, int K) {
+static __global__ void __launch_bounds__(TC_THREADS) tc_gemm_store_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                   float* __restrict__ D, int ldd, int K, int n_fastest) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* tiles = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     TcShared* sh = (TcShared*)(tiles + TC_STAGES * TC_STAGE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * TC_BN;
+    // n_fastest: consecutive CTAs walk the N tiles of ONE row block (they share the A tile through L2); else the M tiles
+    const int m0 = (n_fastest ? blockIdx.y : blockIdx.x) * TC_BM, n0 = (n_fastest ? blockIdx.x : blockIdx.y) * TC_BN;
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { tc_mbar_init(&sh->full[s], 1); tc_mbar_init(&sh->empty[s], 1); }
         tc_mbar_init(&sh->tmem_full, 1);
@@ -199,7 +201,7 @@ struct TcSharedTop {
 };
 #define TC_SMEM_TOP_BYTES (TC_STAGES * TC_STAGE_BYTES + 1024 + 256)
 
-__global__ void __launch_bounds__(TC_THREADS) tc_corr_top_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles,
+static __global__ void __launch_bounds__(TC_THREADS) tc_corr_top_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int ntiles,
                                                                  int K2, int Ldict, int32_t* __restrict__ cand, float* __restrict__ cand_score) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* tiles = (unsigned char*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);

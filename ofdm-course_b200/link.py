@@ -351,6 +351,16 @@ class Context:
         self._chk(self.lib.ofdm_mmse_ce(self.h, self.p(grid_dev), B, S, Nfft, pp, pc.size, pvp, N_carrier, self.p(h_dev), h_dev.shape[-1], self.p(snr), self.p(H)))
         return H
 
+    def mmse_ce_shared(self, grid_dev, Xp, pilot_loc, N_carrier, h_dev, snr_db):
+        """MMSE_CE with ONE impulse response ``h_dev`` (1-D) and ONE SNR for the whole batch (``ofdm_mmse_ce_shared``)."""
+        B, S, Nfft = grid_dev.shape
+        pc, pp = _i32(pilot_loc)
+        pv, pvp = _f64c(np.asarray(Xp, dtype=np.complex128).reshape(pc.size, -1)[:, 0])
+        H = self.empty_c(B, N_carrier)
+        self._chk(self.lib.ofdm_mmse_ce_shared(self.h, self.p(grid_dev), B, S, Nfft, pp, pc.size, pvp, N_carrier, self.p(h_dev), h_dev.numel(),
+                                               float(snr_db), self.p(H)))
+        return H
+
     def interpolate(self, Hp_dev, pilot_loc, N, method):
         B = Hp_dev.shape[0]
         pc, pp = _i32(pilot_loc)

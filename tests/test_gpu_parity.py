@@ -507,3 +507,37 @@ def test_omp_dense_non_dft_dictionary_is_not_mistaken_for_one(G):
         Hr, hr, ir = O.OMP_estimate(Y[b], A, Nfft, K, 20)
         n = int(it[b])
         assert list(idx[b, :n]) == list(ir) and rel_err(H[b].cpu().numpy(), Hr) < 2e-4
+
+
+@pytest.mark.parametrize("comb,B", [(4, 300), (1, 260)])
+def test_mmse_shared_statistics_path_against_oracle(G, comb, B):
+    """ofdm_mmse_ce_shared: one impulse response and one SNR for the whole batch (`Task5_part2.m:176-177`); W = I - Rpp^-1/snr
+    built once and applied by the tcgen05 split-TF32 product.  Against the oracle's dense MMSE_CE per stream (5e-5), and
+    against the per-stream Levinson kernel fed with the replicated statistics."""
+    rng = np.random.default_rng(53 + comb)
+    if comb == 1:
+        p = OC.LinkParams()
+        p.pilotCarriers, p.dataCarriers = O.pilot_layout_percent(1024, 100, 4096, last_gap=1)
+        p.pilotValues, _ = OC.make_pilot_values(1024, 14, "16QAM", 4 / 3, False)
+    else:
+        p = OC.params_task5(comb=comb)
+    Np = len(p.pilotCarriers)
+    htrue, Htrue = O.get_MP_channel_resp(TAPS5, p.Nfft)
+    snr = 17.0
+    Y = np.zeros((B, p.N_symb, p.Nfft), dtype=complex)
+    Y[:, :, :1024] = Htrue[None, None, :1024] * (rng.choice([-1.0, 1.0], (B, p.N_symb, 1024)) * 1.3) + 0.1 * crandn(rng, B, p.N_symb, 1024)
+    Y[:, 0, p.pilotCarriers - 1] = Htrue[p.pilotCarriers - 1] * p.pilotValues[:, 0] + 0.1 * crandn(rng, B, Np)
+    h = np.zeros(64, dtype=complex)
+    h[:len(htrue)] = htrue
+    ctx = G.default_context("f32")
+    Yd = ctx.cplx(Y)
+    H = ctx.mmse_ce_shared(Yd, p.pilotValues, p.pilotCarriers, p.N_carrier, ctx.cplx(h), snr)
+    Hl = ctx.mmse_ce(Yd, p.pilotValues, p.pilotCarriers, p.N_carrier, ctx.cplx(np.tile(h, (B, 1))), snr)
+    ctx.sync()
+    H, Hl = H.cpu().numpy(), Hl.cpu().numpy()
+    errs = []
+    for b in range(0, B, max(1, B // 6)):
+        ref = O.MMSE_CE(Y[b].T, p.pilotValues, p.pilotCarriers, p.Nfft, p.N_carrier, h, snr)
+        errs.append((rel_err(H[b], ref), rel_err(Hl[b], ref)))
+    print('shared vs oracle / levinson vs oracle:', errs, 'shared vs levinson', rel_err(H, Hl))
+    assert max(e[0] for e in errs) < 5e-5 and rel_err(H, Hl) < 5e-5

@@ -30,12 +30,12 @@ int main(int argc, char** argv) {
     cudaFuncSetAttribute(tc_gemm_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     dim3 grid(M / TC_BM, N / TC_BN);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    tc_gemm_store_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(mapA, mapB, dD, N, K);
+    tc_gemm_store_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(mapA, mapB, dD, N, K, 0);
     cudaError_t e = cudaDeviceSynchronize();
     printf("first launch: %s\n", cudaGetErrorString(e));
     if (e != cudaSuccess) return 1;
     cudaEventRecord(e0);
-    for (int i = 0; i < 5; ++i) tc_gemm_store_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(mapA, mapB, dD, N, K);
+    for (int i = 0; i < 5; ++i) tc_gemm_store_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES>>>(mapA, mapB, dD, N, K, 0);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 5;
     std::vector<float> D((size_t)M * N);
