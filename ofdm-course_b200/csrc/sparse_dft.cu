@@ -19,16 +19,13 @@
 #define OD_EPT 16            // dictionary columns per thread: Ldict <= 4096
 #define OD_MAXK 16
 
-// g[d] = sum_i exp(+2*pi*1j*p_i*d/N), exact argument reduction, summed in double
-__global__ void omp_dft_gram_kernel(const int32_t* __restrict__ p0, int Np, int N, double2* __restrict__ g_d, float2* __restrict__ g_f) {
+// g[d] = sum_i exp(+2*pi*1j*p_i*d/N) = sum_i conj(W_N^{(p_i d) mod N}) from the double twiddle table (exact argument reduction)
+__global__ void omp_dft_gram_kernel(const int32_t* __restrict__ p0, int Np, int N, const double2* __restrict__ tw_d, double2* __restrict__ g_d,
+                                    float2* __restrict__ g_f) {
     const int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= N) return;
     double sr = 0, si = 0;
-    for (int i = 0; i < Np; ++i) {
-        double s, c;
-        sincospi(2.0 * (double)((p0[i] * d) & (N - 1)) / (double)N, &s, &c);
-        sr += c; si += s;
-    }
+    for (int i = 0; i < Np; ++i) { const double2 w = tw_d[(p0[i] * d) & (N - 1)]; sr += w.x; si -= w.y; }
     g_d[d] = make_double2(sr, si);
     g_f[d] = make_float2((float)sr, (float)si);
 }
@@ -218,14 +215,16 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         __syncthreads();
         if (s_stop || it == K - 1) break;
         // ---- alpha -= sum_{i<=n} (beta_n T_in) g[(l - c_i) mod N]
+        // (two packed FFMA2 per column: the table value is the broadcast operand, -w and its rotation are hoisted per tap)
         for (int q = 0; q <= nu; ++q) {
             const float2 x = wf[q];
+            const float2 w0 = make_float2(-x.x, -x.y), w1 = make_float2(x.y, -x.x);      // a -= g*x = g.x*(-x) + g.y*(-i x)... (x.y, -x.x) = -i*x negated
             const float2* gp = gS + ((tid - ucol[q]) & Nmask);
 #pragma unroll
             for (int j = 0; j < NG; ++j) {
                 const float2 gv = gp[OD_THREADS * j];
-                a[j].x = fmaf(-x.x, gv.x, fmaf(x.y, gv.y, a[j].x));
-                a[j].y = fmaf(-x.x, gv.y, fmaf(-x.y, gv.x, a[j].y));
+                a[j] = __ffma2_rn(make_float2(gv.x, gv.x), w0, a[j]);
+                a[j] = __ffma2_rn(make_float2(gv.y, gv.y), w1, a[j]);
             }
         }
     }
@@ -271,9 +270,13 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         __syncthreads();
         for (int mm = tid; mm < Nfft; mm += OD_THREADS) {
             const int aa = mm >> 6, bq = mm & 63;
-            float ar = 0, ai = 0;
-            for (int u = 0; u < nu; ++u) { const float2 x = t_hi[64 * u + aa], w = t_lo[64 * u + bq]; ar += x.x * w.x - x.y * w.y; ai += x.x * w.y + x.y * w.x; }
-            Hout[f * (int64_t)Nfft + mm] = make_float2(ar, ai);
+            float2 acc = make_float2(0.f, 0.f);
+            for (int u = 0; u < nu; ++u) {
+                const float2 x = t_hi[64 * u + aa], w = t_lo[64 * u + bq];
+                acc = __ffma2_rn(make_float2(x.x, x.x), w, acc);                        // x * w, x the broadcast operand
+                acc = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), acc);
+            }
+            Hout[f * (int64_t)Nfft + mm] = acc;
         }
     }
 }
@@ -291,7 +294,7 @@ int ofdm_omp_dft(ofdm_ctx* ctx, const void* y, int64_t B, int Np, const int32_t*
     CUDA_TRY(ctx, cudaMallocAsync((void**)&gbuf, (sizeof(double2) + sizeof(float2)) * (size_t)Nfft, ctx->stream));
     double2* g_d = (double2*)gbuf;
     float2* g_f = (float2*)(g_d + Nfft);
-    omp_dft_gram_kernel<<<(Nfft + 127) / 128, 128, 0, ctx->stream>>>(p0_dev, Np, Nfft, g_d, g_f);
+    omp_dft_gram_kernel<<<(Nfft + 63) / 64, 64, 0, ctx->stream>>>(p0_dev, Np, Nfft, tw_d, g_d, g_f);
     const size_t smem = sizeof(float2) * 2 * (size_t)Nfft;
     auto kern = Ldict <= 1024 ? omp_dft_kernel<4> : (Ldict <= 2048 ? omp_dft_kernel<8> : omp_dft_kernel<16>);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
