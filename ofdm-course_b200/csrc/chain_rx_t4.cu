@@ -130,10 +130,7 @@ __global__ void __launch_bounds__(T4_THREADS) rx_t4_kernel(T4Params p, PlanDev<f
             const int lo = min(tid * CH, n), hi = min(lo + CH, n);
             int cmask = 0;
             for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
-            cnt[tid] = cmask;
-            __syncthreads();
-            int rank = 0;
-            for (int k = 0; k < tid; ++k) rank += cnt[k];
+            int rank = block_exclusive_scan(cmask, red_i);      // survivors before this thread's chunk
             double sum = 0; int kept = 0;
             for (int j = max(lo, 1); j < hi; ++j) {
                 double d = fabs(taus[j] - taus[j - 1]);
@@ -437,10 +434,7 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
             const int lo = min(tid * CH, n), hi = min(lo + CH, n);
             int cmask = 0;
             for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
-            cnt[tid] = cmask;
-            __syncthreads();
-            int rank = 0;
-            for (int k = 0; k < tid; ++k) rank += cnt[k];
+            int rank = block_exclusive_scan(cmask, red_i);      // survivors before this thread's chunk
             double sum = 0; int kept = 0;
             for (int j = max(lo, 1); j < hi; ++j) {
                 double d = fabs(taus[j] - taus[j - 1]);
@@ -487,11 +481,14 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         __syncthreads();
         // ---- estimate_channel on the corrected grid + equalize_signal (`estimate_channel.m:4-8`)
         if (p.mp_desync) {
-            for (int q = tid; q < p.Np; q += T4_THREADS) {
+            // mean over the symbols of rx_pilot * cf / tx_pilot (`estimate_channel.m:4-6`): one warp per pilot, lanes over the
+            // symbols, summed in the reference's order only up to FP32 reassociation
+            for (int q = warp; q < p.Np; q += NW) {
                 float sr = 0.f, si = 0.f;
                 const float2 g = G[p.pil0[q]];
-                for (int s = 0; s < p.S; ++s) { float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
-                yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
+                for (int s = lane; s < p.S; s += 32) { const float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
+                sr = warp_sum(sr); si = warp_sum(si);
+                if (lane == 0) yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
             }
             __syncthreads();
             float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
@@ -503,7 +500,7 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
         }
         // ---- get_payload + demapping for the whole stream (decisions alias the tile/taus region, free by now)
         int errs = 0, nears = 0;
-        uint8_t* dec = (uint8_t*)smem_raw;             // [S][Nd] codes
+        uint8_t* dec = (uint8_t*)smem_raw;             // [S][Nd] codes = the stream's symbol order
         __syncthreads();
         for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
             const int cidx = p.data0[dr];
@@ -528,8 +525,46 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
             }
         }
         __syncthreads();
-        // ---- DeScrambler + BER, frame by frame without barriers: a thread packs word wd and its predecessor itself
-        {
+        // ---- DeScrambler + BER
+        if (QAM16 && (stream_bits & 31) == 0 && p.frame_bits >= 64) {
+            // Word-aligned streams: raw stream word w = eight ready-made nibbles dec[8w .. 8w+7] (one 8-byte load); the
+            // descrambler out[i] = raw[i] ^ raw[i-13] ^ raw[i-14] runs on a 64-bit window (previous word : this word).
+            // Frames need not be word aligned (Task 4: 6,640 bits): where a frame starts at offset t inside the window the bits
+            // below it are replaced by the initial register's history (`DeScrambler.m:8-13` with the per-frame reset of
+            // `Main_model_Task_4.m:350-364`), and the word's bits before the boundary keep the previous frame's history.
+            const int words = (int)(stream_bits >> 5);
+            auto raw_word = [&](int w) -> uint32_t {
+                const uint2 by = *reinterpret_cast<const uint2*>(dec + 8 * w);
+                uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
+                uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
+                return lo | (hi << 16);
+            };
+            const uint32_t* tb = txbits ? txbits + b * words : nullptr;
+            uint32_t* ob = outbits ? outbits + b * words : nullptr;
+            for (int w = tid; w < words; w += T4_THREADS) {
+                const uint32_t R = raw_word(w);
+                uint32_t o = R;
+                if (p.scramble) {
+                    const uint32_t P = w ? raw_word(w - 1) : 0u;
+                    const unsigned long long X = ((unsigned long long)R << 32) | P;
+                    o = (uint32_t)((X ^ (X << 13) ^ (X << 14)) >> 32);
+                    const int fl = (32 * w + 31) / p.frame_bits;            // frame of the word's last bit
+                    const int t = fl * p.frame_bits - 32 * w;               // its start relative to this word: (-frame_bits, 31]
+                    if (t > -14) {
+                        const int sh = 32 + t;                              // window position of the frame's first bit, 19..63
+                        const unsigned long long keep = ~0ull << sh;
+                        const unsigned long long hist = sh >= 32 ? ((unsigned long long)p.prev0 << (sh - 32)) : ((unsigned long long)p.prev0 >> (32 - sh));
+                        const unsigned long long Xf = (X & keep) | (hist & ~keep);
+                        const uint32_t of = (uint32_t)((Xf ^ (Xf << 13) ^ (Xf << 14)) >> 32);
+                        const uint32_t before = t > 0 ? ((1u << t) - 1u) : 0u;   // bits of this word that still belong to the previous frame
+                        o = (o & before) | (of & ~before);
+                    }
+                }
+                if (tb) errs += __popc(o ^ tb[w]);
+                if (ob) ob[w] = o;
+            }
+        } else {
+            // generic constellations / unaligned streams: frame by frame, a thread packs word wd and its predecessor itself
             const int fpb = p.SpF * p.Nd;              // decisions per frame
             auto packed = [&](const uint8_t* fr, int wd) -> uint32_t {
                 uint32_t word = 0;

@@ -91,6 +91,20 @@ template <typename V> __device__ __forceinline__ V block_sum(V v, V* red) {
     r = warp_sum(r);
     return r;
 }
+// exclusive prefix sum of one int per thread over the block (blockDim.x a multiple of 32, <= 1024); `sh` >= 32 ints of
+// shared scratch.  Two barriers inside; the result is valid in every thread.
+__device__ __forceinline__ int block_exclusive_scan(int v, int* sh) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();
+    if (lane == 31) sh[w] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < w; ++k) base += sh[k];
+    return base + incl - v;
+}
 __device__ __forceinline__ int block_min(int v, int* red) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     v = warp_min(v);

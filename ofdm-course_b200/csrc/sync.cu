@@ -389,10 +389,7 @@ __global__ void __launch_bounds__(FS_THREADS) fine_sync_est_kernel(const cx<T>* 
     const int lo = min(tid * CH, n), hi = min(lo + CH, n);
     int c = 0;
     for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); c += (d < 1e-3 && d != 0.0); }
-    cnt[tid] = c;
-    __syncthreads();
-    int rank = 0;
-    for (int k = 0; k < tid; ++k) rank += cnt[k];
+    int rank = block_exclusive_scan(c, cnt);            // survivors before this thread's chunk
     double sum = 0; int kept = 0;
     for (int j = max(lo, 1); j < hi; ++j) {
         double d = fabs(taus[j] - taus[j - 1]);
