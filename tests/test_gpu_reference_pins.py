@@ -46,7 +46,7 @@ def test_P1_ber_snr_curve_on_gpu(G, cname):
         c = res["counts"].cpu().numpy()
         assert c[1] == B * p.stream_bits
         ber = c[0] / c[1]
-        assert abs(ber / fig - 1) < RP.ber_tolerance(fig), (cname, snr, ber, fig)
+        assert abs(ber / fig - 1) < RP.ber_tolerance(fig, cname), (cname, snr, ber, fig)
 
 
 def test_P2_mer_at_25dB_on_gpu(G):
