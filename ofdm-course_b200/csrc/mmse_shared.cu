@@ -37,6 +37,14 @@ __global__ void mmse_stats_kernel(const cx<T>* __restrict__ h, int h_len, double
     }
 }
 
+// rows[b][0..n) = src[0..n) for every b: the shared impulse response replicated for the per-stream solver
+__global__ void mmse_replicate_kernel(const unsigned char* __restrict__ src, size_t row_bytes, int64_t B, unsigned char* __restrict__ rows,
+                                      double* __restrict__ snr, double snr_db) {
+    const int64_t b = blockIdx.x;
+    for (size_t i = threadIdx.x; i < row_bytes; i += blockDim.x) rows[b * row_bytes + i] = src[i];
+    if (threadIdx.x == 0) snr[b] = snr_db;
+}
+
 __device__ __forceinline__ void ms_block_sum4(double v[4], double (*red)[4]) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -145,12 +153,11 @@ extern "C" int ofdm_mmse_ce_shared(ofdm_ctx* ctx, const void* grid, int64_t B, i
         // general path: replicate the shared statistics and run the per-stream solver
         const size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
         unsigned char* tmp = nullptr;
-        CUDA_TRY(ctx, cudaMallocAsync((void**)&tmp, esz * (size_t)h_len * B + sizeof(double) * B, ctx->stream));
-        std::vector<double> snr((size_t)B, snr_db);
-        double* snr_d = (double*)(tmp + esz * (size_t)h_len * B);
-        cudaMemcpyAsync(snr_d, snr.data(), sizeof(double) * B, cudaMemcpyHostToDevice, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);               // `snr` is a host temporary
-        cudaMemcpy2DAsync(tmp, esz * h_len, h, 0, esz * h_len, (size_t)B, cudaMemcpyDeviceToDevice, ctx->stream);
+        const size_t rows_b = (esz * (size_t)h_len * B + 15) / 16 * 16;
+        CUDA_TRY(ctx, cudaMallocAsync((void**)&tmp, rows_b + sizeof(double) * B, ctx->stream));
+        double* snr_d = (double*)(tmp + rows_b);
+        mmse_replicate_kernel<<<(unsigned)B, 64, 0, ctx->stream>>>((const unsigned char*)h, esz * (size_t)h_len, B, tmp, snr_d, snr_db);
+        ctx->launches++;
         int rc = ofdm_mmse_ce(ctx, grid, B, S, Nfft, loc, Np, pv, Nc, tmp, h_len, snr_d, H);
         cudaFreeAsync(tmp, ctx->stream);
         return rc;

@@ -541,3 +541,18 @@ def test_mmse_shared_statistics_path_against_oracle(G, comb, B):
         errs.append((rel_err(H[b], ref), rel_err(Hl[b], ref)))
     print('shared vs oracle / levinson vs oracle:', errs, 'shared vs levinson', rel_err(H, Hl))
     assert max(e[0] for e in errs) < 5e-5 and rel_err(H, Hl) < 5e-5
+
+
+@pytest.mark.parametrize("prec,B", [("f64", 5), ("f32", 7)])
+def test_mmse_shared_statistics_general_path(G, prec, B):
+    """ofdm_mmse_ce_shared outside the tensor-core regime (FP64 contexts, small batches): the shared h / SNR are replicated
+    for the per-stream Levinson solver; same result as ofdm_mmse_ce and as the oracle."""
+    rng = np.random.default_rng(59)
+    p, bits, rx, Y = _task5_Y(rng, 4, snr=15)
+    h = np.fft.ifft(O.LS_CE(Y, p.pilotValues, p.pilotCarriers, p.N_carrier))
+    ctx = G.default_context(prec)
+    Yd = ctx.cplx(np.tile(np.ascontiguousarray(Y.T)[None], (B, 1, 1)))
+    H = ctx.mmse_ce_shared(Yd, p.pilotValues, p.pilotCarriers, p.N_carrier, ctx.cplx(h), 15.0).cpu().numpy()
+    ref = O.MMSE_CE(Y, p.pilotValues, p.pilotCarriers, p.Nfft, p.N_carrier, h, 15.0)
+    for b in range(B):
+        assert rel_err(H[b], ref) < (1e-9 if prec == "f64" else 5e-5)
