@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=8192)
     ap.add_argument("--m5-streams", type=int, default=8192, help="streams per SNR point of the Task-5 sweep record (0 = skip)")
     ap.add_argument("--m5-streams-t4", type=int, default=2048, help="streams per SNR point of the Task-4 (STO/CFO) sweep record (0 = skip)")
-    ap.add_argument("--m5-tile", type=int, default=2048)
+    ap.add_argument("--m5-tile", type=int, default=8192)
     ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--ref-streams", type=int, default=200, help="distinct streams per host process in the CPU sample")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="RX-chain time per host process in the CPU sample")

@@ -311,6 +311,8 @@ OFDM_API int ofdm_rx_chain_t4_ex(ofdm_ctx*, const ofdm_link_params*, const void*
  * add_STO -> add_CFO -> multipath -> M2 RX chain with AutoCorrFunction / remove_IFO / fine_sync / estimate_channel).
  * Streams are numbered globally, g = snr_index * streams_per_point + j; payload bits, noise, STO and CFO draws are
  * Philox streams keyed by (seed, g), so the integer counters are identical for every (rank, world, tile) split.
+ * The payload is drawn in the scrambled domain: the Philox words of ofdm_payload_bits are the scrambled frames s and the
+ * payload is p = DeScrambler(s) (uniform, and Scrambler(p) = s exactly), so the transmitter maps s without scrambling.
  * One call processes the rank-th of `world` equal contiguous shares of the global stream range (ofdm_sweep_share)
  * and ADDS into counts_dev: n_snr x 4 int64, row i = {bit errors, bits, symbols within near_eps of a decision
  * boundary, guard-interval detector failures (Task-4 chain)}.  The caller sums the rows of all ranks -- the path's
@@ -322,7 +324,7 @@ typedef struct ofdm_sweep_params {
     int32_t n_snr;
     const double* snr_db_host;   /* n_snr SNR points in dB */
     int64_t streams_per_point;
-    int64_t tile_streams;        /* streams per work item; 0 = 2048 */
+    int64_t tile_streams;        /* streams per work item; 0 = 8192 (two signal buffers of tile x stream bytes are allocated) */
     int32_t rank, world;         /* share of the global stream range this call processes */
     uint64_t seed;
     const double* taps_host;     /* n_taps x 2 doubles (delay, amplitude), row-major; n_taps = 0: no multipath */

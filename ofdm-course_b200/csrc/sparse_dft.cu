@@ -316,13 +316,13 @@ int ofdm_omp_probe_dft(ofdm_ctx* ctx, const void* A, int Np, int Ldict, int Nfft
     if (ctx->precision != OFDM_PREC_F32 || Ldict < 2) return OFDM_OK;
     int32_t* buf = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync((void**)&buf, sizeof(int32_t) * ((size_t)Np + 1), ctx->stream));
-    int32_t one = 1, flag = 0;
-    CUDA_TRY(ctx, cudaMemcpyAsync(buf + Np, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t flag = 0;
+    CUDA_TRY(ctx, cudaMemsetAsync(buf + Np, 0xFF, sizeof(int32_t), ctx->stream));    // all ones: cleared by the first mismatch
     omp_dft_probe_kernel<<<Np, 128, 0, ctx->stream>>>((const float2*)A, Np, Ldict, Nfft, buf, buf + Np);
     ctx->launches++;
     CUDA_TRY(ctx, cudaMemcpyAsync(&flag, buf + Np, sizeof flag, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flag == 1) { *is_dft = true; *p0_out = buf; }
+    if (flag != 0) { *is_dft = true; *p0_out = buf; }
     else cudaFreeAsync(buf, ctx->stream);
     return OFDM_OK;
 }

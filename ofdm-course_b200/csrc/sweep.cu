@@ -12,8 +12,16 @@
 // counters do not depend on the number of ranks or on the tile size.  No data-path collective: the caller adds the
 // counters of all ranks (one int64 all-reduce).  Everything is enqueued on the context's stream without any host
 // synchronisation; the signal buffers are stream-ordered temporaries reused by every tile.
+//
+// The payload is drawn in the SCRAMBLED domain: the Philox words are the scrambled frames s, and the payload the chain is
+// run on is p = DeScrambler(s) -- uniform because the scrambler is a bijection per frame, and Scrambler(p) = s exactly, so
+// the TX chain on p with its scrambler IS the TX chain on s without it (checked bit for bit in
+// tests/test_gpu_chain.py).  The three-tap descrambler runs at memory speed on 5 KB per stream, whereas the scrambler
+// inside the TX kernel is eleven log-depth doublings per frame, a quarter of that kernel's time.
 #include "common.cuh"
 #include "philox.cuh"
+
+uint32_t ofdm_reg_to_prev(const uint8_t* reg);
 
 // payload words: word w of stream g = 32 Philox bits, counter (w/4, g), own key space
 __global__ void payload_bits_kernel(uint32_t* __restrict__ bits, int64_t n_streams, int64_t words, uint64_t seed, int64_t first_stream) {
@@ -42,6 +50,32 @@ __global__ void draw_sto_cfo_kernel(int64_t B, uint64_t seed, int64_t first_stre
     // multiply-shift maps a 32-bit word uniformly onto {0..m} (bias < 2^-21 for m <= 2048)
     if (nsto) nsto[b] = (int32_t)(((uint64_t)c[0] * (uint64_t)(sto_max + 1)) >> 32);
     if (cfo) cfo[b] = (double)(((uint64_t)c[1] * (uint64_t)(cfo_int_max + 1)) >> 32) + ((double)c[2] * 2.3283064365386963e-10 - 0.5);
+}
+
+// p = DeScrambler(s) for word-aligned streams, one thread per output word: out[i] = s[i] ^ s[i-13] ^ s[i-14] on a 64-bit
+// window (previous word : this word); where a frame starts inside the window the bits below it are the initial register's
+// history (`DeScrambler.m:8-13` with the per-frame reset of `Main_model_Task_4.m:350-364`).  Frames need not be word aligned.
+__global__ void descramble_streams_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n_words, int words_per_stream,
+                                          int frame_bits, uint32_t prev0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const int w = (int)(i % words_per_stream);                 // word inside its stream (streams are word aligned)
+    const uint32_t R = in[i];
+    const uint32_t P = w ? in[i - 1] : 0u;
+    const unsigned long long X = ((unsigned long long)R << 32) | P;
+    uint32_t o = (uint32_t)((X ^ (X << 13) ^ (X << 14)) >> 32);
+    const int fl = (32 * w + 31) / frame_bits;                  // frame of the word's last bit
+    const int t = fl * frame_bits - 32 * w;                     // its start relative to this word: (-frame_bits, 31]
+    if (t > -14) {
+        const int sh = 32 + t;
+        const unsigned long long keep = ~0ull << sh;
+        const unsigned long long hist = sh >= 32 ? ((unsigned long long)prev0 << (sh - 32)) : ((unsigned long long)prev0 >> (32 - sh));
+        const unsigned long long Xf = (X & keep) | (hist & ~keep);
+        const uint32_t of = (uint32_t)((Xf ^ (Xf << 13) ^ (Xf << 14)) >> 32);
+        const uint32_t before = t > 0 ? ((1u << t) - 1u) : 0u;
+        o = (o & before) | (of & ~before);
+    }
+    out[i] = o;
 }
 
 __global__ void fill_double_kernel(double* __restrict__ p, int64_t n, double v) {
@@ -99,7 +133,7 @@ extern "C" int ofdm_sweep_ber(ofdm_ctx* ctx, const ofdm_link_params* lp, const o
     const int64_t words = stream_bits / 32;
     const int64_t L = (int64_t)lp->S * (lp->Nfft + lp->Tg);
     const size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
-    int64_t tile = sp->tile_streams > 0 ? sp->tile_streams : 2048;
+    int64_t tile = sp->tile_streams > 0 ? sp->tile_streams : 8192;    // whole tiles of 8,192 streams keep the persistent kernels' tails below 1 %
     tile = std::min<int64_t>(tile, sp->streams_per_point);
 
     // multipath impulse response on the device (`get_MP_channel_resp.m:2-19`), in the context's complex type
@@ -129,12 +163,18 @@ extern "C" int ofdm_sweep_ber(ofdm_ctx* ctx, const ofdm_link_params* lp, const o
     const size_t small_b = (sizeof(double) * 3 + sizeof(int32_t) * 2) * (size_t)tile + 256;
     unsigned char* pool = nullptr;
     const size_t sig_al = (sig_b + 255) / 256 * 256, bits_al = (bits_b + 255) / 256 * 256;
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&pool, sig_al * (t4 ? 3 : 2) + bits_al + small_b, ctx->stream));
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&pool, sig_al * (t4 ? 3 : 2) + 2 * bits_al + small_b, ctx->stream));
     void* tx = pool;
     void* rx = pool + sig_al;
     void* tmp = t4 ? (void*)(pool + 2 * sig_al) : nullptr;
-    uint32_t* bits = (uint32_t*)(pool + sig_al * (t4 ? 3 : 2));
+    uint32_t* sbits = (uint32_t*)(pool + sig_al * (t4 ? 3 : 2));            // scrambled frames s (Philox)
+    uint32_t* bits = (uint32_t*)((unsigned char*)sbits + bits_al);          // payload p = DeScrambler(s): the reference bits
     double* snr_d = (double*)((unsigned char*)bits + bits_al);
+    ofdm_link_params lp_tx = *lp;                                           // the TX side maps s directly
+    lp_tx.scramble = 0;
+    const int64_t frames = lp->S / lp->SpF, frame_bits = stream_bits / frames;
+    if (!lp->scramble) bits = sbits;                                        // no scrambler in the chain: p = s
+    const uint32_t prev0 = ofdm_reg_to_prev(lp->reg0_host);
     double* psum = snr_d + tile;
     double* cfo_d = psum + tile;
     int32_t* sto_d = (int32_t*)(cfo_d + tile);
@@ -147,18 +187,24 @@ extern "C" int ofdm_sweep_ber(ofdm_ctx* ctx, const ofdm_link_params* lp, const o
         const int64_t i = g / sp->streams_per_point;                              // SNR point of this tile
         const int64_t n = std::min<int64_t>(std::min<int64_t>(tile, g_end - g), (i + 1) * sp->streams_per_point - g);
         int64_t* row = counts_dev + 4 * i;
-        rc = ofdm_payload_bits(ctx, bits, n, words, sp->seed, g);
+        rc = ofdm_payload_bits(ctx, sbits, n, words, sp->seed, g);
+        if (rc == OFDM_OK && lp->scramble) {
+            if (frame_bits >= 64) {
+                descramble_streams_kernel<<<(unsigned)cdiv64(n * words, 256), 256, 0, ctx->stream>>>(sbits, bits, n * words, (int)words, (int)frame_bits, prev0);
+                ctx->launches++;
+            } else rc = ofdm_descramble(ctx, sbits, bits, n * frames, frame_bits, lp->reg0_host, nullptr);
+        }
         if (rc) break;
         fill_double_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, ctx->stream>>>(snr_d, n, sp->snr_db_host[i]);
         ctx->launches++;
         if (!t4) {
             // Task 5 order: Noise, then multipath (`Main_model_Task_5.m:108,123-127`)
-            rc = ofdm_tx_chain_p(ctx, lp, bits, n, tx, psum);
+            rc = ofdm_tx_chain_p(ctx, &lp_tx, sbits, n, tx, psum);
             if (rc == OFDM_OK) rc = ofdm_channel_t5_p(ctx, tx, n, L, snr_d, psum, nullptr, sp->seed, g, h_dev, D, rx);
             if (rc == OFDM_OK) rc = ofdm_rx_chain_t5(ctx, lp, rx, n, bits, nullptr, nullptr, row, nullptr, sp->near_eps);
         } else {
             // Task 4 order: Noise -> add_STO -> add_CFO -> multipath (`Main_model_Task_4.m:95,103,110,263-264`)
-            rc = ofdm_tx_chain(ctx, lp, bits, n, tx);
+            rc = ofdm_tx_chain(ctx, &lp_tx, sbits, n, tx);
             if (rc == OFDM_OK) rc = ofdm_add_noise(ctx, tx, n, L, snr_d, nullptr, sp->seed, g, rx, nullptr);
             if (rc == OFDM_OK) rc = ofdm_draw_sto_cfo(ctx, n, sp->seed, g, sp->sto_max, sp->cfo_int_max, sto_d, cfo_d);
             if (rc == OFDM_OK) rc = ofdm_add_sto(ctx, rx, n, L, sto_d, tmp);

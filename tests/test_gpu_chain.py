@@ -231,8 +231,8 @@ def test_sweep_counts_do_not_depend_on_the_split(G, chain):
 
 
 def test_sweep_task5_equals_the_composed_calls(G):
-    """ofdm_sweep_ber (chain 0) == ofdm_payload_bits -> ofdm_tx_chain_p -> ofdm_channel_t5_p -> ofdm_rx_chain_t5 with the same
-    keys, each of which is compared with the oracle elsewhere in this file."""
+    """ofdm_sweep_ber (chain 0) == ofdm_payload_bits -> DeScrambler -> ofdm_tx_chain_p -> ofdm_channel_t5_p -> ofdm_rx_chain_t5 with
+    the same keys, each of which is compared with the oracle elsewhere in this file."""
     import torch
     from ofdm_b200 import sweep
     p = OC.params_task5(comb=4)
@@ -242,10 +242,17 @@ def test_sweep_task5_equals_the_composed_calls(G):
     got = sweep.ber_sweep(ctx, lp, snrs, spp, TAPS5, "task5", seed=seed, tile=4, near_eps=1e-3)
     hd = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
     words = p.stream_bits // 32
+    lp_raw = _lp(ctx, p, scramble=False)
     for i, snr in enumerate(snrs):
-        bits = torch.zeros(spp * words, dtype=torch.int32, device=ctx.device)
-        ctx._chk(ctx.lib.ofdm_payload_bits(ctx.h, ctx.p(bits), spp, words, seed, i * spp))
+        sbits = torch.zeros(spp * words, dtype=torch.int32, device=ctx.device)
+        ctx._chk(ctx.lib.ofdm_payload_bits(ctx.h, ctx.p(sbits), spp, words, seed, i * spp))
+        # the sweep draws the SCRAMBLED frames s; the payload is p = DeScrambler(s), and the TX chain on p equals the chain on s
+        # without its scrambler bit for bit (Scrambler(p) = s)
+        bits = ctx.scramble(sbits, spp * p.Amount_OFDM_Frames, p.frame_bits, descramble=True)
+        assert torch.equal(ctx.scramble(bits, spp * p.Amount_OFDM_Frames, p.frame_bits), sbits)
         tx, psum = ctx.tx_chain(lp, bits, spp, want_power=True)
+        tx_raw = ctx.tx_chain(lp_raw, sbits, spp)
+        assert torch.equal(torch.view_as_real(tx), torch.view_as_real(tx_raw))
         rx = ctx.channel_t5(tx, snr_db=snr, h_dev=hd, seed=seed, first_stream_id=i * spp, power_sum=psum)
         res = ctx.rx_chain_t5(lp, rx, spp, tx_bits_dev=bits, near_eps=1e-3)
         ctx.sync()
@@ -277,8 +284,9 @@ def test_sweep_task4_against_oracle(G):
     hd = ctx.cplx(O.get_MP_channel_resp(TAPS4, p.Nfft)[0])
     for i, snr in enumerate(snrs):
         g0 = i * spp
-        bits = torch.zeros(spp * words, dtype=torch.int32, device=ctx.device)
-        ctx._chk(ctx.lib.ofdm_payload_bits(ctx.h, ctx.p(bits), spp, words, seed, g0))
+        sbits = torch.zeros(spp * words, dtype=torch.int32, device=ctx.device)
+        ctx._chk(ctx.lib.ofdm_payload_bits(ctx.h, ctx.p(sbits), spp, words, seed, g0))
+        bits = ctx.scramble(sbits, spp * p.Amount_OFDM_Frames, p.frame_bits, descramble=True)       # payload p = DeScrambler(s)
         sto = torch.zeros(spp, dtype=torch.int32, device=ctx.device)
         cfo = torch.zeros(spp, dtype=torch.float64, device=ctx.device)
         ctx._chk(ctx.lib.ofdm_draw_sto_cfo(ctx.h, spp, seed, g0, p.Nfft + p.T_Guard, 30, ctx.p(sto), ctx.p(cfo)))
