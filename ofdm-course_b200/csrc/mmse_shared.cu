@@ -177,15 +177,16 @@ extern "C" int ofdm_mmse_ce_shared(ofdm_ctx* ctx, const void* grid, int64_t B, i
     cudaStream_t st = ctx->stream;
     float *At = nullptr, *Bt = nullptr, *D = nullptr;
     double* stats = nullptr;
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&At, sizeof(float) * (size_t)Bpad * 3 * K2, st));
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&Bt, sizeof(float) * (size_t)2 * Npad * 3 * K2, st));
     const int Kt = 3 * K2;                                 // whole K of the split product
     const int Ks = 768;                                    // K per slice = 96 tcgen05.mma steps per accumulator
     const int n_slices = (Kt + Ks - 1) / Ks;               // Kt is a multiple of 384; the last slice may be half a slice
     const size_t slice_stride = (size_t)Bpad * 2 * Npad;
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&D, sizeof(float) * slice_stride * n_slices, st));
-    CUDA_TRY(ctx, cudaMallocAsync((void**)&stats, 2 * sizeof(double), st));
-    CUDA_TRY(ctx, cudaMemsetAsync(Bt, 0, sizeof(float) * (size_t)2 * Npad * 3 * K2, st));
+    // one stream-ordered allocation for the four temporaries (one failure point, one release)
+    const size_t at_b = sizeof(float) * (size_t)Bpad * 3 * K2, bt_b = sizeof(float) * (size_t)2 * Npad * 3 * K2, d_b = sizeof(float) * slice_stride * n_slices;
+    unsigned char* pool = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&pool, at_b + bt_b + d_b + 64, st));
+    At = (float*)pool; Bt = (float*)(pool + at_b); D = (float*)(pool + at_b + bt_b); stats = (double*)(pool + at_b + bt_b + d_b);
+    if (cudaMemsetAsync(Bt, 0, bt_b, st) != cudaSuccess) { cudaFreeAsync(pool, st); return ctx_fail(ctx, OFDM_ERR_CUDA, "memset failed"); }
     mmse_stats_kernel<float><<<1, 256, 0, st>>>((const float2*)h, h_len, (double)(loc[1] - loc[0]), Nc, snr_db, stats);
     const size_t wsm = 4 * sizeof(double2) * (size_t)Np;
     int rc = OFDM_OK;
@@ -215,6 +216,6 @@ extern "C" int ofdm_mmse_ce_shared(ofdm_ctx* ctx, const void* grid, int64_t B, i
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "shared-statistics MMSE launch failed: %s", cudaGetErrorString(e));
     }
-    cudaFreeAsync(At, st); cudaFreeAsync(Bt, st); cudaFreeAsync(D, st); cudaFreeAsync(stats, st);
+    cudaFreeAsync(pool, st);
     return rc;
 }
