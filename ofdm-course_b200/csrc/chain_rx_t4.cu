@@ -610,6 +610,318 @@ __global__ void __launch_bounds__(T4_THREADS, 2) rx_t4_fast_kernel(T4Params p, T
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Split form of the fast path (large batches): the same arithmetic as rx_t4_fast_kernel in three kernels, so that each
+// part runs at its own occupancy instead of sharing one 128-register, two-CTA-per-SM persistent kernel:
+//   t4_ifo_kernel    one warp per stream: remove_IFO's search (`remove_IFO.m:5-8`)
+//   t4_sym_kernel    one CTA per (stream, eight symbols): derotation + 1024-point DFT per warp, no block barrier after the
+//                    rotation table; writes the N_carrier kept bins and the pilots of every symbol
+//   t4_post_kernel   one CTA per stream, few registers: fine_sync estimators, channel estimate, decisions, DeScrambler, BER
+// The kept bins travel through global memory (N_carrier x S complex per stream) instead of a per-CTA L2 parking area.
+__device__ __forceinline__ void t4_load_window(const float2* __restrict__ r, int64_t L, int SL, int64_t n0, int tg, bool tshift, int lane, float2* v) {
+    constexpr int N = 1024;
+    const int64_t m0 = tshift ? n0 - SL + tg : n0;          // sample n of the corrected stream is r[n - SL + tg] for n >= SL, else 0 (`add_STO.m:5-9`)
+    const bool all_in = (m0 >= 0 && m0 + N <= L && (!tshift || n0 >= SL));
+    if (all_in) {
+        const float2* q = r + m0 + lane;
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) v[n1] = ldg_stream(q + 32 * n1);
+    } else {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) {
+            const int64_t m = m0 + 32 * n1 + lane;
+            const bool ok = m >= 0 && m < L && (!tshift || n0 + 32 * n1 + lane >= SL);
+            v[n1] = ok ? ldg_stream(r + m) : make_float2(0.f, 0.f);
+        }
+    }
+}
+__device__ __forceinline__ void t4_pass_a(float2* v, float2* E, const float2* __restrict__ tw_t, int lane) {   // DFT over n1, twiddle, transpose
+    fft32<32>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) {
+        float2 x = v[k1];
+        if (k1) x = cmul(x, __ldg(tw_t + 32 * k1 + lane));
+        E[k1 * T4F_EROW + lane] = x;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) v[n2] = E[lane * T4F_EROW + n2];
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(T4_THREADS) t4_ifo_kernel(T4FastExtra fx, const float2* __restrict__ rx, int64_t B, int64_t L, int Tg, int time_desync,
+                                                            const int32_t* __restrict__ tg_pos, const double* __restrict__ freq_off,
+                                                            int32_t* __restrict__ ifo_out) {
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t b = (int64_t)blockIdx.x * (T4_THREADS / 32) + warp;
+    if (b >= B) return;
+    float2* E = (float2*)smem_raw + warp * 32 * T4F_EROW;
+    const double fo = freq_off[b];
+    float2 v[32];
+    t4_load_window(rx + b * L, L, N + Tg, (int64_t)N, time_desync ? tg_pos[b] : 0, time_desync != 0, lane, v);
+#pragma unroll
+    for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], rot_from_cycles(fo * (double)(32 * n1 + lane) / N));   // the window's constant phase does not change magnitudes
+    t4_pass_a(v, E, fx.tw_t, lane);
+    fft32<32>(v);
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int k2 = 31; k2 >= 0; --k2) {
+        const double re = v[k2].x, im = v[k2].y;
+        if (sqrt(re * re + im * im) > 0.77) first = lane + 32 * k2;
+    }
+    first = warp_min(first);
+    if (lane == 0) ifo_out[b] = (first == 0x7fffffff) ? -1 : first;
+}
+
+template <int K2N>
+__global__ void __launch_bounds__(T4_THREADS, 2) t4_sym_kernel(T4Params p, T4FastExtra fx, const float2* __restrict__ rx, int64_t B, int64_t L, int groups,
+                                                               const int32_t* __restrict__ tg_pos, const double* __restrict__ freq_off,
+                                                               const int32_t* __restrict__ ifo_in, float2* __restrict__ Ysc_all, float2* __restrict__ Yp_all) {
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = T4_THREADS / 32;
+    float2* tiles = (float2*)smem_raw;
+    float2* wtab = tiles + NW * 32 * T4F_EROW;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.x / groups;
+    const int g = (int)(blockIdx.x - b * groups);
+    const int SL = N + p.Tg;
+    const int tg = p.time_desync ? tg_pos[b] : 0;
+    const int ifo = p.freq_desync ? ifo_in[b] : 0;
+    const double c = (p.freq_desync ? freq_off[b] : 0.0) + (ifo > 0 ? ifo : 0);     // total derotation in cycles per Nfft samples
+    if (p.freq_desync) {
+        for (int i = tid; i < N; i += T4_THREADS) wtab[i] = rot_from_cycles(c * (double)i / N);
+        __syncthreads();
+    }
+    const int s = NW * g + warp;
+    if (s >= p.S) return;
+    float2* E = tiles + warp * 32 * T4F_EROW;
+    float2 v[32];
+    t4_load_window(rx + b * L, L, SL, (int64_t)s * SL + p.Tg, tg, p.time_desync != 0, lane, v);
+    if (p.freq_desync) {
+#pragma unroll
+        for (int n1 = 0; n1 < 32; ++n1) v[n1] = cmul(v[n1], wtab[32 * n1 + lane]);
+    }
+    t4_pass_a(v, E, fx.tw_t, lane);
+    fft32<K2N>(v);
+    const float2 rs = p.freq_desync ? rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / N) : make_float2(1.f, 0.f);
+    float2* Yo = Ysc_all + ((int64_t)b * p.S + s) * p.Nc;
+#pragma unroll
+    for (int k2 = 0; k2 < K2N; ++k2) {
+        const int k = lane + 32 * k2;
+        const float2 y = p.freq_desync ? cmul(v[k2], rs) : v[k2];
+        E[k] = y;                                                  // natural order, for the pilot gather below
+        if (k < p.Nc) Yo[k] = y;
+    }
+    __syncwarp();
+    float2* Po = Yp_all + ((int64_t)b * p.S + s) * p.Np;
+    for (int q = lane; q < p.Np; q += 32) Po[q] = E[p.pil0[q]];
+}
+
+template <bool QAM16, bool NEAR>
+__global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4FastExtra fx, PlanDev<float> plan, DevConst<float> con, int64_t B,
+                                                                const float2* __restrict__ Ysc_all, const float2* __restrict__ Yp_all,
+                                                                const uint32_t* __restrict__ txbits, int64_t total_bits, uint32_t* __restrict__ outbits,
+                                                                unsigned long long* __restrict__ counts, double* __restrict__ tau_out,
+                                                                double* __restrict__ phase_out, float2* __restrict__ Hout, float near_eps) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double red[32];
+    __shared__ int red_i[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = T4_THREADS / 32;
+    const int M = p.Np * p.S;
+    // layout: [taus | decisions] (aliased), Yp, G, yk, dk
+    const size_t taus_bytes = sizeof(double) * (size_t)M, dec_bytes = (size_t)p.S * p.Nd;
+    double* taus = (double*)smem_raw;
+    float2* Yp = (float2*)(smem_raw + ((taus_bytes > dec_bytes ? taus_bytes : dec_bytes) + 15) / 16 * 16);
+    float2* G = Yp + M;
+    float2* yk = G + p.Nc;
+    float2* dk = yk + plan.n_knots;
+    const int fw = (p.frame_bits + 31) >> 5;
+    const int64_t b = blockIdx.x;
+    const float2* Ysc = Ysc_all + b * (int64_t)p.S * p.Nc;
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    {
+        const float2* src = Yp_all + b * (int64_t)M;
+        for (int i = tid; i < M; i += T4_THREADS) Yp[i] = src[i];
+    }
+    __syncthreads();
+    // ---- fine_sync estimators (`Task 4/fine_sync.m:25-35,47-52`), products in double, angles in FP32 (as in the fused kernel)
+    double tau = 0.0, phase = 0.0;
+    if (p.time_desync || p.freq_desync) {
+        const double deltak = (double)(p.pil0[1] - p.pil0[0]);
+        auto q_at = [&](int i) -> double2 { return cmulc(p.pilots_d[i], to_d(Yp[i])); };
+        auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return (double)atan2f((float)d.y, (float)d.x) / (2.0 * CUDART_PI * deltak); };
+        const int n = M - 1;
+        for (int j = tid; j < n; j += T4_THREADS) taus[j] = tau_at(j);
+        __syncthreads();
+        const int CH = (n + T4_THREADS - 1) / T4_THREADS;
+        const int lo = min(tid * CH, n), hi = min(lo + CH, n);
+        int cmask = 0;
+        for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
+        int rank = block_exclusive_scan(cmask, red_i);
+        double sum = 0; int kept = 0;
+        for (int j = max(lo, 1); j < hi; ++j) {
+            double d = fabs(taus[j] - taus[j - 1]);
+            if (d < 1e-3 && d != 0.0) { if (rank >= p.Np) { sum += taus[j]; ++kept; } ++rank; }
+        }
+        sum = block_sum(sum, red);
+        double nk = block_sum((double)kept, red);
+        tau = sum / nk;
+        double2* prot = (double2*)taus;
+        __syncthreads();
+        for (int q = tid; q < p.Np; q += T4_THREADS) {
+            double sn = 0.0, cs = 1.0;
+            if (p.time_desync) sincospi(2.0 * tau * (double)p.pil0[q], &sn, &cs);
+            prot[q] = make_double2(cs, sn);
+        }
+        __syncthreads();
+        double ps = 0; int pn = 0;
+        for (int i = tid; i < M; i += T4_THREADS) {
+            const int pq = i % p.Np;
+            double2 rxv = to_d(Yp[i]);
+            if (p.time_desync) rxv = cmul(rxv, prot[pq]);
+            double2 qq = cmulc(p.pilots_d[i], rxv);
+            double a = (double)atan2f((float)qq.y, (float)qq.x);
+            if (fabs(a) > 1e-3) { ps += a; ++pn; }
+        }
+        ps = block_sum(ps, red);
+        double pk = block_sum((double)pn, red);
+        phase = ps / pk;
+        if (tid == 0) { if (tau_out) tau_out[b] = tau; if (phase_out) phase_out[b] = phase; }
+    }
+    for (int k = tid; k < p.Nc; k += T4_THREADS) {
+        double sn = 0.0, cs = 1.0;
+        if (p.time_desync || p.freq_desync) {
+            double ang = (p.time_desync ? 2.0 * tau * (double)k : 0.0);
+            double s1, c1, s2 = 0.0, c2 = 1.0;
+            sincospi(ang, &s1, &c1);
+            if (p.freq_desync) sincos(phase, &s2, &c2);
+            cs = c1 * c2 - s1 * s2; sn = s1 * c2 + c1 * s2;
+        }
+        G[k] = make_float2((float)cs, (float)sn);
+    }
+    __syncthreads();
+    if (p.mp_desync) {
+        for (int q = warp; q < p.Np; q += NW) {
+            float sr = 0.f, si = 0.f;
+            const float2 g = G[p.pil0[q]];
+            for (int s = lane; s < p.S; s += 32) { const float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
+            sr = warp_sum(sr); si = warp_sum(si);
+            if (lane == 0) yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
+        }
+        __syncthreads();
+        float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
+        plan_apply_fn<float>(plan, yk, dk, [&](int k, float2 h) {
+            if (Hrow) Hrow[k] = h;
+            G[k] = cdiv(G[k], h);
+        });
+        __syncthreads();
+    }
+    int errs = 0, nears = 0;
+    uint8_t* dec = (uint8_t*)smem_raw;
+    __syncthreads();
+    for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
+        const int cidx = p.data0[dr];
+        const bool in = cidx < p.Nc;
+        const float2 g = in ? G[cidx] : make_float2(0.f, 0.f);
+        const float2* Yc = Ysc + (in ? cidx : 0);
+        for (int s0 = 0; s0 < p.S; s0 += 10) {
+            float2 y[10];
+#pragma unroll
+            for (int u = 0; u < 10; ++u) y[u] = (s0 + u < p.S) ? ldg_stream(Yc + (int64_t)(s0 + u) * p.Nc) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 10; ++u)
+                if (s0 + u < p.S) {
+                    const float2 e = in ? cmul(y[u], g) : make_float2(0.f, 0.f);
+                    float margin = 1.f;
+                    uint32_t code;
+                    if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
+                    else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                    if (NEAR && margin < near_eps) ++nears;
+                    dec[(s0 + u) * p.Nd + dr] = (uint8_t)code;
+                }
+        }
+    }
+    __syncthreads();
+    if (QAM16 && (stream_bits & 31) == 0 && p.frame_bits >= 64) {     // word-aligned streams: see rx_t4_fast_kernel
+        const int words = (int)(stream_bits >> 5);
+        auto raw_word = [&](int w) -> uint32_t {
+            const uint2 by = *reinterpret_cast<const uint2*>(dec + 8 * w);
+            uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
+            uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
+            return lo | (hi << 16);
+        };
+        const uint32_t* tb = txbits ? txbits + b * words : nullptr;
+        uint32_t* ob = outbits ? outbits + b * words : nullptr;
+        for (int w = tid; w < words; w += T4_THREADS) {
+            const uint32_t R = raw_word(w);
+            uint32_t o = R;
+            if (p.scramble) {
+                const uint32_t P = w ? raw_word(w - 1) : 0u;
+                const unsigned long long X = ((unsigned long long)R << 32) | P;
+                o = (uint32_t)((X ^ (X << 13) ^ (X << 14)) >> 32);
+                const int fl = (32 * w + 31) / p.frame_bits;
+                const int t = fl * p.frame_bits - 32 * w;
+                if (t > -14) {
+                    const int sh = 32 + t;
+                    const unsigned long long keep = ~0ull << sh;
+                    const unsigned long long hist = sh >= 32 ? ((unsigned long long)p.prev0 << (sh - 32)) : ((unsigned long long)p.prev0 >> (32 - sh));
+                    const unsigned long long Xf = (X & keep) | (hist & ~keep);
+                    const uint32_t of = (uint32_t)((Xf ^ (Xf << 13) ^ (Xf << 14)) >> 32);
+                    const uint32_t before = t > 0 ? ((1u << t) - 1u) : 0u;
+                    o = (o & before) | (of & ~before);
+                }
+            }
+            if (tb) errs += __popc(o ^ tb[w]);
+            if (ob) ob[w] = o;
+        }
+    } else {
+        const int fpb = p.SpF * p.Nd;
+        auto packed = [&](const uint8_t* fr, int wd) -> uint32_t {
+            uint32_t word = 0;
+            if (QAM16) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const int q = 8 * wd + j; if (q < fpb) word |= (uint32_t)fr[q] << (4 * j); }
+            } else {
+                const int b0 = 32 * wd, b1 = min(b0 + 32, p.frame_bits);
+                for (int q = b0 / p.bps; q * p.bps < b1; ++q) {
+                    int idx = fr[q];
+                    for (int i = 0; i < p.bps; ++i) {
+                        int pos = q * p.bps + i;
+                        if (pos >= b0 && pos < b1 && ((idx >> (p.bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                    }
+                }
+            }
+            return word;
+        };
+        for (int item = tid; item < p.frames * fw; item += T4_THREADS) {
+            const int f = item / fw, wd = item - f * fw;
+            const uint8_t* fr = dec + (size_t)f * fpb;
+            const uint32_t cw = packed(fr, wd);
+            uint32_t o = cw;
+            if (p.scramble) {
+                const uint32_t prev = wd ? packed(fr, wd - 1) : p.prev0;
+                o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
+            }
+            const int n = min(32, p.frame_bits - 32 * wd);
+            if (n < 32) o &= (1u << n) - 1u;
+            const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+            if (txbits) errs += __popc(o ^ bits_get32(txbits, base + 32 * (int64_t)wd, min(total_bits, base + p.frame_bits)));
+            if (outbits) bits_put(outbits, base + 32 * (int64_t)wd, n, o);
+        }
+    }
+    errs = block_sum(errs, red_i);
+    nears = block_sum(nears, red_i);
+    if (tid == 0 && counts) {
+        if (errs) atomicAdd(&counts[0], (unsigned long long)errs);
+        atomicAdd(&counts[1], (unsigned long long)stream_bits);
+        if (nears) atomicAdd(&counts[2], (unsigned long long)nears);
+    }
+}
+
 extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_t L, int W, int Nfft, void* autocorr, int32_t* tg_pos, double* freq_off,
                                 int32_t* fail);
 
@@ -695,7 +1007,49 @@ extern "C" int ofdm_rx_chain_t4_ex(ofdm_ctx* ctx, const ofdm_link_params* lp, co
                                            : (near ? rx_t4_fast_kernel<13, false, true> : rx_t4_fast_kernel<13, false, false>))
                                     : (q16 ? (near ? rx_t4_fast_kernel<32, true, true> : rx_t4_fast_kernel<32, true, false>)
                                            : (near ? rx_t4_fast_kernel<32, false, true> : rx_t4_fast_kernel<32, false, false>));
-                if (fx.tw_t) {
+                // large batches: the same arithmetic as three kernels, each at its own occupancy (t4_ifo / t4_sym / t4_post)
+                const int64_t SPLIT_CHUNK = 16384;                      // streams per pass: 2.6 GB of kept bins at the Task-4 shape
+                const bool aligned = stream_bits % 32 == 0;
+                const size_t post_smem = (std::max(taus, (size_t)p.S * p.Nd) + 15) / 16 * 16 + sizeof(float2) * ((size_t)p.S * p.Np + p.Nc + 2 * (size_t)pl->n_knots) + 32;
+                const size_t sym_smem = tiles + sizeof(float2) * 1024;
+                if (fx.tw_t && B >= 512 && (aligned || B <= SPLIT_CHUNK) && post_smem <= 100 * 1024 && !getenv("OFDM_B200_T4_FUSED")) {
+                    const int64_t CH = std::min<int64_t>(B, SPLIT_CHUNK);
+                    const int groups = (p.S + T4_THREADS / 32 - 1) / (T4_THREADS / 32);
+                    float2* bins = nullptr;
+                    cudaError_t e = cudaMallocAsync((void**)&bins, sizeof(float2) * (size_t)CH * p.S * ((size_t)p.Nc + p.Np), ctx->stream);
+                    if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "cudaMallocAsync failed: %s", cudaGetErrorString(e));
+                    float2* Ysc_all = bins;
+                    float2* Yp_all = bins + (size_t)CH * p.S * p.Nc;
+                    int32_t* ifo_ptr = ifo_dev ? ifo_dev : tg_s + B;      // the scratch holds two int32 per stream
+                    if (rc == OFDM_OK && !freq_desync && ifo_dev) cudaMemsetAsync(ifo_dev, 0, sizeof(int32_t) * B, ctx->stream);
+                    typedef void (*post_t)(T4Params, T4FastExtra, PlanDev<float>, DevConst<float>, int64_t, const float2*, const float2*, const uint32_t*, int64_t,
+                                           uint32_t*, unsigned long long*, double*, double*, float2*, float);
+                    post_t post = q16 ? (near ? t4_post_kernel<true, true> : t4_post_kernel<true, false>) : (near ? t4_post_kernel<false, true> : t4_post_kernel<false, false>);
+                    auto symk = small ? t4_sym_kernel<13> : t4_sym_kernel<32>;
+                    cudaFuncSetAttribute(t4_ifo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles);
+                    cudaFuncSetAttribute(symk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sym_smem);
+                    cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem);
+                    const int64_t words = stream_bits / 32;
+                    for (int64_t c0 = 0; c0 < B && rc == OFDM_OK; c0 += CH) {
+                        const int64_t nb = std::min(CH, B - c0);
+                        const float2* rxc = (const float2*)rx + c0 * L;
+                        if (freq_desync) {
+                            t4_ifo_kernel<<<(unsigned)cdiv64(nb, T4_THREADS / 32), T4_THREADS, tiles, ctx->stream>>>(fx, rxc, nb, L, p.Tg, time_desync, tg_dev + c0, fo_dev + c0, ifo_ptr + c0);
+                            ctx->launches++;
+                        }
+                        symk<<<(unsigned)(nb * groups), T4_THREADS, sym_smem, ctx->stream>>>(p, fx, rxc, nb, L, groups, tg_dev + c0, fo_dev + c0, ifo_ptr + c0, Ysc_all, Yp_all);
+                        post<<<(unsigned)nb, T4_THREADS, post_smem, ctx->stream>>>(p, fx, plan_dev<float>(pl), make_devconst<float>(lp->constellation), nb, Ysc_all, Yp_all,
+                                                                                   tx_bits ? tx_bits + c0 * words : nullptr, nb * stream_bits,
+                                                                                   out_bits ? out_bits + c0 * words : nullptr, (unsigned long long*)counts,
+                                                                                   tau_dev ? tau_dev + c0 : nullptr, phase_dev ? phase_dev + c0 : nullptr,
+                                                                                   H_dev ? (float2*)H_dev + c0 * p.Nc : nullptr, (float)near_eps);
+                        ctx->launches += 2;
+                        e = cudaGetLastError();
+                        if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "split Task-4 chain launch failed: %s", cudaGetErrorString(e));
+                    }
+                    if (bins) cudaFreeAsync(bins, ctx->stream);
+                    fast_done = true;
+                } else if (fx.tw_t) {
                     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem);
                     kern<<<grid, T4_THREADS, fsmem, ctx->stream>>>(p, fx, plan_dev<float>(pl), make_devconst<float>(lp->constellation), (const float2*)rx, B, L, tg_dev, fo_dev,
                                                                    (float2*)scr, tx_bits, B * stream_bits, out_bits, (unsigned long long*)counts, ifo_dev, tau_dev,

@@ -109,12 +109,15 @@ __device__ __forceinline__ float4 f4add(float4 a, float4 b) {
 template <bool ALIGNED>
 __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* __restrict__ rx, int64_t L, int W, int Nfft, int64_t n_out, int tile,
                                                                   float2* __restrict__ ac_out, uint32_t* __restrict__ flags, int64_t flag_words,
-                                                                  const int32_t* __restrict__ gate) {
+                                                                  const int32_t* __restrict__ list, const int32_t* __restrict__ n_list) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int NE = AC_THREADS * AC_G;                 // samples staged per block
     float4* Q = (float4*)smem_raw;                    // NE + NE/16 entries
-    const int64_t b = blockIdx.x;
-    if (gate && gate[b] == 0) return;                 // second (full-length) scan: only streams the prefix scan left unresolved
+    // `list` (second, full-length scan): blockIdx.x is a slot that walks the streams the prefix scan left unresolved -- a
+    // handful at most, so the grid is a few hundred slots instead of one CTA per stream and tile
+    const int n_it = list ? *n_list : 1;
+    for (int it = list ? (int)blockIdx.x : 0; it < n_it; it += list ? (int)gridDim.x : 1) {
+    const int64_t b = list ? list[it] : blockIdx.x;
     const int64_t n0 = (int64_t)blockIdx.y * tile;
     const float2* r = rx + b * L;
     const int tid = threadIdx.x;
@@ -197,12 +200,15 @@ __global__ void __launch_bounds__(AC_THREADS) autocorr_f32_kernel(const float2* 
         const int64_t wi = (n0 + tid * AC_G) >> 5;
         if (wi < flag_words) flags[b * flag_words + wi] = mask16 | (hi << 16);
     }
+    if (list) __syncthreads();                        // the staging area is reused by the slot's next stream
+    }
 }
 
 template <typename T>
 __global__ void autocorr_detect_kernel(const cx<T>* __restrict__ rx, int64_t B, int64_t L, int W, int Nfft, int64_t n_out,
                                        const uint32_t* __restrict__ flags, int64_t flag_words, int32_t* __restrict__ tg_pos,
-                                       double* __restrict__ freq_off, int32_t* __restrict__ fail, const int32_t* __restrict__ gate) {
+                                       double* __restrict__ freq_off, int32_t* __restrict__ fail, const int32_t* __restrict__ gate,
+                                       int32_t* __restrict__ list, int32_t* __restrict__ n_list) {
     const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (b >= B) return;
@@ -250,6 +256,7 @@ __global__ void autocorr_detect_kernel(const cx<T>* __restrict__ rx, int64_t B, 
         tg_pos[b] = tg;
         freq_off[b] = -atan2(ni / den, nr / den) / (2.0 * CUDART_PI);
         if (fail) fail[b] = failed;
+        if (list && failed) list[atomicAdd(n_list, 1)] = (int32_t)b;      // prefix scan: unresolved streams for the full-length pass
     }
 }
 
@@ -271,20 +278,26 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
     const int64_t n_prefix = cdiv64(3 * (int64_t)(Nfft + W), tile) * tile;
     const bool two_stage = autocorr == nullptr && n_prefix < n_out && !getenv("OFDM_B200_FULL_AUTOCORR");
     const int64_t flag_words = (n_out + 31) / 32;
-    uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words + sizeof(int32_t) * B + 64);
+    uint32_t* flags = (uint32_t*)ctx_scratch(ctx, sizeof(uint32_t) * B * flag_words + sizeof(int32_t) * (2 * B + 1) + 64);
     REQUIRE(ctx, flags != nullptr, "scratch allocation failed");
     int32_t* fail_s = (int32_t*)(flags + B * flag_words);
+    int32_t* list = fail_s + B;                           // unresolved streams of the prefix scan, then their count
+    int32_t* n_list = list + B;
     if (two_stage && !fail) fail = fail_s;
+    if (two_stage) CUDA_TRY(ctx, cudaMemsetAsync(n_list, 0, sizeof(int32_t), ctx->stream));
     for (int stage = two_stage ? 0 : 1; stage < 2; ++stage) {
         const int64_t n_scan = stage == 0 ? n_prefix : n_out;
         const int64_t fw = (n_scan + 31) / 32;
         const int tiles = (int)cdiv64(n_scan, tile);
-        const int32_t* gate = (two_stage && stage == 1) ? fail : nullptr;
+        const bool second = two_stage && stage == 1;
+        const int32_t* gate = second ? fail : nullptr;
         DISPATCH_T(ctx, {
             size_t smem = 4 * sizeof(T) * (size_t)(AC_THREADS * AC_G + AC_THREADS);
             if constexpr (std::is_same<T, float>::value) {
                 auto k1 = (W & 15) ? autocorr_f32_kernel<false> : autocorr_f32_kernel<true>;
-                k1<<<dim3((unsigned)B, tiles), AC_THREADS, smem, ctx->stream>>>((const float2*)rx, L, W, Nfft, n_scan, tile, (float2*)autocorr, flags, fw, gate);
+                const unsigned gx = second ? (unsigned)std::min<int64_t>(B, 256) : (unsigned)B;
+                k1<<<dim3(gx, tiles), AC_THREADS, smem, ctx->stream>>>((const float2*)rx, L, W, Nfft, n_scan, tile, (float2*)autocorr, flags, fw,
+                                                                        second ? list : nullptr, second ? n_list : nullptr);
             } else {
                 auto k1 = (W & 15) ? autocorr_kernel<T, false> : autocorr_kernel<T, true>;
                 if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -292,7 +305,8 @@ extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_
             }
             ctx->launches++;
             autocorr_detect_kernel<T><<<(unsigned)cdiv64(B * 32, 128), 128, 0, ctx->stream>>>((const cx<T>*)rx, B, L, W, Nfft, n_scan, flags, fw,
-                                                                                                tg_pos, freq_off, fail, gate);
+                                                                                                tg_pos, freq_off, fail, gate,
+                                                                                                (two_stage && stage == 0) ? list : nullptr, n_list);
         });
         LAUNCH_CHECK(ctx);
     }

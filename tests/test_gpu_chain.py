@@ -570,3 +570,49 @@ def test_persistent_wraparound_against_oracle(G):
     assert counts[1] == B * p.stream_bits and counts[0] == int(eps.sum())
     assert mism <= 3 * p.bps * counts[2]
     assert abs(int(counts[0]) - ref_err) <= mism
+
+
+def test_rx_chain_task4_split_path_matches_fused_and_oracle(G, monkeypatch):
+    """Batches of 512 streams and more run the Task-4 chain as three kernels (t4_ifo / t4_sym / t4_post) instead of the fused
+    persistent one: same integer estimates, same decisions up to near-boundary symbols, against the fused kernel for every
+    stream and against the oracle for the distinct cases."""
+    TAPS4 = [[0, 1], [4, .6], [10, .3]]
+    p = OC.params_task4()
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(19)
+    cases = [(37, 7.24), (900, 0.24), (150, 12.4), (0, 0.0), (611, 3.3), (1152, 30.4), (1, 0.49), (77, 21.7)]
+    bits = rng.integers(0, 2, (len(cases), p.stream_bits)).astype(np.uint8)
+    rxs, refs = [], []
+    for b, (sto, cfo) in enumerate(cases):
+        tx, _, _ = OC.tx_chain(p, bits[b], fast=True)
+        rx = OC.impair_task4(p, tx, SNR_dB=28, Time_Delay=sto, Freq_Shift=cfo, taps=TAPS4, rng=rng)
+        rxs.append(rx)
+        refs.append(OC.rx_chain_task4(p, rx, bits[b]))
+    B = 520                                              # 65 copies of the eight cases: >= 512 selects the split path
+    reps = B // len(cases)
+    rx_d = ctx.cplx(np.tile(np.stack(rxs), (reps, 1)))
+    bd = ctx.bits(np.tile(bits, (reps, 1)).ravel())
+    l0 = ctx.launches
+    split = ctx.rx_chain_t4_fused(lp, rx_d, tx_bits_dev=bd, near_eps=1e-3, want_H=True)
+    ctx.sync()
+    n_split = ctx.launches - l0
+    monkeypatch.setenv("OFDM_B200_T4_FUSED", "1")
+    l0 = ctx.launches
+    fused = ctx.rx_chain_t4_fused(lp, rx_d, tx_bits_dev=bd, near_eps=1e-3, want_H=True)
+    ctx.sync()
+    assert n_split == 4 + 3 and ctx.launches - l0 == 4 + 1          # autocorrelation (2 + gated 2) + ifo / sym / post vs one fused kernel
+    for key in ("TgPosition", "IFO", "fail"):
+        assert np.array_equal(split[key].cpu().numpy(), fused[key].cpu().numpy()), key
+    ts, tf = split["tau"].cpu().numpy(), fused["tau"].cpu().numpy()
+    ok = np.isfinite(tf)
+    assert np.array_equal(np.isfinite(ts), ok) and np.max(np.abs(ts[ok] - tf[ok])) < 1e-6
+    gs = ctx.host_bits(split["bits"], B * p.stream_bits).reshape(B, -1)
+    gf = ctx.host_bits(fused["bits"], B * p.stream_bits).reshape(B, -1)
+    near = int(split["counts"][2].item()) + int(fused["counts"][2].item())
+    assert int(np.sum(gs != gf)) <= 3 * p.bps * near
+    for b in range(len(cases)):
+        assert np.array_equal(gs[b], gs[b + 8 * (reps - 1)])                                  # copies decode alike
+        assert split["TgPosition"][b].item() == refs[b]["TgPosition"] and split["IFO"][b].item() == refs[b]["IFO"]
+    mism = sum(int(np.sum(gs[b] != refs[b]["bits"])) for b in range(len(cases)) if np.all(np.isfinite(refs[b]["H"][:400])))
+    assert mism * reps <= 3 * p.bps * int(split["counts"][2].item())
