@@ -66,6 +66,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of a block that a later bulk copy will fetch (no shared memory, no completion to wait for)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Work item q of this CTA = (stream blockIdx.x + (q / S) * gridDim.x, symbol q % S).  Symbols are
@@ -87,15 +91,19 @@ __host__ __device__ constexpr int mask_perm(int m, int j) {
     for (int i = 0; i < 16; ++i) if (!((m >> i) & 1)) { if (n == j) return i; ++n; }
     return 0;
 }
-template <bool QAM16, bool NEAR, int MASK>
-__global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
+// SLIM: three CTAs per SM instead of two.  One symbol buffer per CTA (the next symbol is fetched as soon as pass C has read
+// the current one, and lands during pass C's arithmetic, the decisions and whatever the two co-resident CTAs are doing) and
+// two-level twiddles: W^{t k1} = W^{t (k1 & 3)} * W^{4 t (k1 >> 2)} from six resident values per pass instead of fifteen,
+// at the price of nine extra complex multiplications per pass -- 85 registers and 61 KB of shared memory per CTA.
+template <bool QAM16, bool NEAR, int MASK, bool SLIM>
+__global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
                                                                int32_t* __restrict__ err_stream, float near_eps) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[2];
     float2* xb0 = (float2*)smem_raw;            // two 4096-sample symbol buffers (ring)
-    float2* Hinv = xb0 + 2 * XBUF;              // 1024
+    float2* Hinv = xb0 + (SLIM ? 1 : 2) * XBUF; // 1024
     float2* yk = Hinv + 1024;                   // n_knots
     float2* dk = yk + plan.n_knots;             // n_knots
     int32_t* slot_s = (int32_t*)(dk + plan.n_knots);   // 1024
@@ -106,15 +114,31 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     for (int i = tid; i < 1024; i += FX_THREADS) slot_s[i] = p.slot[i];
     for (int i = tid; i < p.Np; i += FX_THREADS) { float2 x = p.pilots[i]; float dd = x.x * x.x + x.y * x.y; pinv[i] = make_float2(x.x / dd, -x.y / dd); }
 
-    // per-thread twiddles, resident for the whole kernel
-    float2 ta[16], tb[16];
+    // per-thread twiddles, resident for the whole kernel.  SLIM keeps W^{t c}, W^{4 t d} (c, d = 1..3) per pass and multiplies
+    // twice; the full table is one value per output.
+    constexpr int NTW = SLIM ? 4 : 16;
+    float2 ta[NTW], tb[NTW];                      // SLIM: [c] = W^{t c}
+    float2 ta4[SLIM ? 4 : 1], tb4[SLIM ? 4 : 1];  // SLIM: [d] = W^{4 t d}
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) ta[k1] = p.tw4096[(tid * k1) & 4095];             // W4096^{t*k1}, t = 16 n2 + n3
+    for (int k1 = 0; k1 < NTW; ++k1) ta[k1] = p.tw4096[(tid * k1) & 4095];             // W4096^{t*k1}, t = 16 n2 + n3
     {
         const int n3 = tid & 15;
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) tb[k2] = p.tw4096[(16 * n3 * k2) & 4095];     // W256^{n3*k2}
+        for (int k2 = 0; k2 < NTW; ++k2) tb[k2] = p.tw4096[(16 * n3 * k2) & 4095];     // W256^{n3*k2}
+        if (SLIM) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) { ta4[d] = p.tw4096[(4 * tid * d) & 4095]; tb4[d] = p.tw4096[(64 * n3 * d) & 4095]; }
+        }
     }
+    // x * (twiddle of output k = c + 4 d)
+    auto twa = [&](float2 x, int c, int d) -> float2 {
+        if (SLIM) { if (c) x = cmul(x, ta[c]); if (d) x = cmul(x, ta4[d]); return x; }
+        return (c + 4 * d) ? cmul(x, ta[SLIM ? 0 : c + 4 * d]) : x;
+    };
+    auto twb = [&](float2 x, int c, int d) -> float2 {
+        if (SLIM) { if (c) x = cmul(x, tb[c]); if (d) x = cmul(x, tb4[d]); return x; }
+        return (c + 4 * d) ? cmul(x, tb[SLIM ? 0 : c + 4 * d]) : x;
+    };
     const int symlen = 4096 + p.Tg;
     const int64_t stream_words = (int64_t)p.frame_words * p.frames;
     const float two_a = p.two_a;
@@ -160,7 +184,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
         else pf_ptr += symlen;
     };
     if (tid == 0) {
-        for (int i = 0; i < 2 && i < n_items; ++i) {
+        for (int i = 0; i < (SLIM ? 1 : 2) && i < n_items; ++i) {
             mbar_expect_tx(&bars[i], 32768u);
             bulk_g2s(xb0 + i * XBUF, pf_ptr, 32768u, &bars[i]);
             pf_advance();
@@ -172,11 +196,11 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
     int64_t b = blockIdx.x;
     uint32_t parity = 0;
     for (int64_t q = 0; q < n_items; ++q) {
-        const int cur = (int)(q & 1);
+        const int cur = SLIM ? 0 : (int)(q & 1);
         float2* X = xb0 + cur * XBUF;
         float2 v[16];
         mbar_wait(&bars[cur], parity);
-        parity ^= (uint32_t)cur;                   // flips after both buffers have been used once
+        parity ^= SLIM ? 1u : (uint32_t)cur;       // flips after every buffer has been used once
 #pragma unroll
         for (int n1 = 0; n1 < 16; ++n1) v[n1] = X[256 * n1 + tid];
         // ---- pass A: DFT over n1 (register index n1 = 4a+b), twiddle W4096^{t*k1}, in place
@@ -191,11 +215,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     const int k1 = c + 4 * d;
-                    if (!((MASK >> k1) & 1)) {
-                        float2 x = v[4 * c + d];
-                        if (k1) x = cmul(x, ta[k1]);
-                        X[k1 * 256 + tid] = x;
-                    }
+                    if (!((MASK >> k1) & 1)) X[k1 * 256 + tid] = twa(v[4 * c + d], c, d);
                 }
         } else {
             fft16(v);
@@ -204,9 +224,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
                 for (int d = 0; d < 4; ++d) {
                     const int k1 = c + 4 * d;
-                    float2 x = v[4 * c + d];
-                    if (k1) x = cmul(x, ta[k1]);
-                    X[k1 * 256 + tid] = x;
+                    X[k1 * 256 + tid] = twa(v[4 * c + d], c, d);
                 }
         }
         __syncthreads();
@@ -228,9 +246,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
 #pragma unroll
                     for (int d = 0; d < 4; ++d) {
                         const int k2 = c + 4 * d;
-                        float2 x = v[4 * c + d];
-                        if (k2) x = cmul(x, tb[k2]);
-                        wp[XGRP * k2] = x;
+                        wp[XGRP * k2] = twb(v[4 * c + d], c, d);
                     }
             }
         }
@@ -247,14 +263,24 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
             }
         }
         __syncthreads();                           // buffer `cur` is free: refill it with item q+2
-        if (tid == 0 && q + 2 < n_items) {
+        if (tid == 0 && q + (SLIM ? 1 : 2) < n_items) {
             fence_proxy_async();
             mbar_expect_tx(&bars[cur], 32768u);
-            bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
-            pf_advance();
+            if (SLIM) {     // the item after this one: next symbol of the stream, or symbol 0 of this CTA's next stream (no carried cursor)
+                const bool wrap = s + 1 == p.S;
+                const float2* nxt = rx + (b + (wrap ? (int64_t)gridDim.x : 0)) * stream_stride + (int64_t)(wrap ? 0 : s + 1) * symlen + p.Tg;
+                bulk_g2s(X, nxt, 32768u, &bars[cur]);
+                if (q + 2 < n_items) {      // and the one after that into L2: with a single buffer the copy above is on the critical path
+                    const int s2 = s + 2 >= p.S ? s + 2 - p.S : s + 2;
+                    bulk_prefetch_l2(rx + (b + (s + 2 >= p.S ? (int64_t)gridDim.x : 0)) * stream_stride + (int64_t)s2 * symlen + p.Tg, 32768u);
+                }
+            } else {
+                bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
+                pf_advance();
+            }
         }
         uint32_t txw[4] = {0u, 0u, 0u, 0u};
-        if (sf == p.SpF - 1 && txbits) {           // reference words of this frame, consumed ~400 instructions later
+        if (!SLIM && sf == p.SpF - 1 && txbits) {  // reference words of this frame, consumed ~400 instructions later
             const uint32_t* tp = txbits + b * stream_words + (int64_t)f * p.frame_words + tid;
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = ldg_once(tp + FX_THREADS * j);
@@ -335,7 +361,7 @@ __global__ void __launch_bounds__(FX_THREADS, 2) rx4096_kernel(Fast4096Params p,
                         const uint32_t prev = w ? packed(w - 1) : p.prev0;
                         o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18));
                     }
-                    if (txbits) errs += __popc(o ^ txw[j]);
+                    if (txbits) errs += __popc(o ^ (SLIM ? ldg_once(txbits + wbase + w) : txw[j]));
                     if (outbits) stg_once(outbits + wbase + w, o);
                 }
             }
@@ -408,11 +434,18 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     typedef void (*kern_t)(Fast4096Params, PlanDev<float>, DevConst<float>, const float2*, int64_t, const uint32_t*, uint32_t*, float2*, unsigned long long*,
                            int32_t*, float);
     kern_t kern;
-    if (q16 && (dead & 0x1111) == 0x1111) kern = near ? rx4096_kernel<true, true, 0x1111> : rx4096_kernel<true, false, 0x1111>;     // comb 4, 4m
-    else if (q16 && (dead & 0x0101) == 0x0101) kern = near ? rx4096_kernel<true, true, 0x0101> : rx4096_kernel<true, false, 0x0101>;  // comb 8, 8m
-    else kern = q16 ? (near ? rx4096_kernel<true, true, 0> : rx4096_kernel<true, false, 0>) : (near ? rx4096_kernel<false, true, 0> : rx4096_kernel<false, false, 0>);
+    const size_t smem_slim = smem - sizeof(float2) * XBUF;
+    const bool slim = getenv("OFDM_B200_NO_SLIM") == nullptr && smem_slim <= 74 * 1024;
+    if (q16 && (dead & 0x1111) == 0x1111) {      // comb 4, 4m
+        if (slim) kern = near ? rx4096_kernel<true, true, 0x1111, true> : rx4096_kernel<true, false, 0x1111, true>;
+        else kern = near ? rx4096_kernel<true, true, 0x1111, false> : rx4096_kernel<true, false, 0x1111, false>;
+    } else if (q16 && (dead & 0x0101) == 0x0101) kern = near ? rx4096_kernel<true, true, 0x0101, false> : rx4096_kernel<true, false, 0x0101, false>;  // comb 8, 8m
+    else kern = q16 ? (near ? rx4096_kernel<true, true, 0, false> : rx4096_kernel<true, false, 0, false>)
+                    : (near ? rx4096_kernel<false, true, 0, false> : rx4096_kernel<false, false, 0, false>);
+    const bool use_slim = slim && q16 && (dead & 0x1111) == 0x1111;
+    if (use_slim) smem = smem_slim;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * 2);
+    int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * (use_slim ? 3 : 2));
     if (err_stream) CUDA_TRY(ctx, cudaMemsetAsync(err_stream, 0, sizeof(int32_t) * B, ctx->stream));
     DevConst<float> con = make_devconst<float>(lp->constellation);
     PlanDev<float> pd = plan_dev<float>(pl);
