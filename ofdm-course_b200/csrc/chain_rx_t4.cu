@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(T4_THREADS) t4_ifo_kernel(T4FastExtra fx, cons
 template <int K2N>
 __global__ void __launch_bounds__(T4_THREADS, 2) t4_sym_kernel(T4Params p, T4FastExtra fx, const float2* __restrict__ rx, int64_t B, int64_t L, int groups,
                                                                const int32_t* __restrict__ tg_pos, const double* __restrict__ freq_off,
-                                                               const int32_t* __restrict__ ifo_in, float2* __restrict__ Ysc_all, float2* __restrict__ Yp_all) {
+                                                               const int32_t* __restrict__ ifo_in, float2* __restrict__ Yd_all, float2* __restrict__ Yp_all) {
     constexpr int N = 1024;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = T4_THREADS / 32;
@@ -707,42 +707,51 @@ __global__ void __launch_bounds__(T4_THREADS, 2) t4_sym_kernel(T4Params p, T4Fas
     t4_pass_a(v, E, fx.tw_t, lane);
     fft32<K2N>(v);
     const float2 rs = p.freq_desync ? rot_from_cycles(c * (double)((int64_t)s * SL + p.Tg) / N) : make_float2(1.f, 0.f);
-    float2* Yo = Ysc_all + ((int64_t)b * p.S + s) * p.Nc;
 #pragma unroll
     for (int k2 = 0; k2 < K2N; ++k2) {
-        const int k = lane + 32 * k2;
         const float2 y = p.freq_desync ? cmul(v[k2], rs) : v[k2];
-        E[k] = y;                                                  // natural order, for the pilot gather below
-        if (k < p.Nc) Yo[k] = y;
+        E[lane + 32 * k2] = (lane + 32 * k2 < p.Nc) ? y : make_float2(0.f, 0.f);      // natural order, for the two gathers below (`get_payload.m`, pilots)
     }
     __syncwarp();
+    // data carriers in payload order, pilots in pilot order: the post kernel reads both linearly
+    float2* Yo = Yd_all + ((int64_t)b * p.S + s) * p.Nd;
+    if ((p.Nd & 1) == 0) {
+        const int2* d2 = reinterpret_cast<const int2*>(p.data0);
+        for (int h = lane; 2 * h < p.Nd; h += 32) {
+            const int2 c = __ldg(d2 + h);
+            const float2 y0 = c.x < 32 * K2N ? E[c.x] : make_float2(0.f, 0.f), y1 = c.y < 32 * K2N ? E[c.y] : make_float2(0.f, 0.f);
+            reinterpret_cast<float4*>(Yo)[h] = make_float4(y0.x, y0.y, y1.x, y1.y);
+        }
+    } else {
+        for (int dr = lane; dr < p.Nd; dr += 32) { const int c = p.data0[dr]; Yo[dr] = c < 32 * K2N ? E[c] : make_float2(0.f, 0.f); }
+    }
     float2* Po = Yp_all + ((int64_t)b * p.S + s) * p.Np;
     for (int q = lane; q < p.Np; q += 32) Po[q] = E[p.pil0[q]];
 }
 
 template <bool QAM16, bool NEAR>
-__global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4FastExtra fx, PlanDev<float> plan, DevConst<float> con, int64_t B,
-                                                                const float2* __restrict__ Ysc_all, const float2* __restrict__ Yp_all,
+__global__ void __launch_bounds__(T4_THREADS, 4) t4_post_kernel(T4Params p, T4FastExtra fx, PlanDev<float> plan, DevConst<float> con, int64_t B,
+                                                                const float2* __restrict__ Yd_all, const float2* __restrict__ Yp_all,
                                                                 const uint32_t* __restrict__ txbits, int64_t total_bits, uint32_t* __restrict__ outbits,
                                                                 unsigned long long* __restrict__ counts, double* __restrict__ tau_out,
                                                                 double* __restrict__ phase_out, float2* __restrict__ Hout, float near_eps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
     __shared__ int red_i[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = T4_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int M = p.Np * p.S;
-    // layout: [taus | decisions] (aliased), Yp, G, yk, dk
-    const size_t taus_bytes = sizeof(double) * (size_t)M, dec_bytes = (size_t)p.S * p.Nd;
-    double* taus = (double*)smem_raw;
-    float2* Yp = (float2*)(smem_raw + ((taus_bytes > dec_bytes ? taus_bytes : dec_bytes) + 15) / 16 * 16);
+    // layout: region A = [angles (float) | rotations | decisions / raw words] (aliased in time), Yp (later: partial sums, then Gd), G, yk, dk
+    const size_t ang_bytes = sizeof(float) * (size_t)M, rot_bytes = sizeof(double2) * (size_t)p.Np, dec_bytes = (size_t)p.S * p.Nd;
+    float* ang = (float*)smem_raw;
+    float2* Yp = (float2*)(smem_raw + (max(max(ang_bytes, rot_bytes), max(dec_bytes, sizeof(float2) * (size_t)T4_THREADS)) + 15) / 16 * 16);
     float2* G = Yp + M;
     float2* yk = G + p.Nc;
     float2* dk = yk + plan.n_knots;
     const int fw = (p.frame_bits + 31) >> 5;
     const int64_t b = blockIdx.x;
-    const float2* Ysc = Ysc_all + b * (int64_t)p.S * p.Nc;
+    const float2* Yd = Yd_all + b * (int64_t)p.S * p.Nd;
     const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    const int step_q = T4_THREADS % p.Np;                    // pilot index of item i = tid + T4_THREADS * j, advanced without a division
     {
         const float2* src = Yp_all + b * (int64_t)M;
         for (int i = tid; i < M; i += T4_THREADS) Yp[i] = src[i];
@@ -751,26 +760,33 @@ __global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4Fa
     // ---- fine_sync estimators (`Task 4/fine_sync.m:25-35,47-52`), products in double, angles in FP32 (as in the fused kernel)
     double tau = 0.0, phase = 0.0;
     if (p.time_desync || p.freq_desync) {
-        const double deltak = (double)(p.pil0[1] - p.pil0[0]);
+        const double inv_c = 1.0 / (2.0 * CUDART_PI * (double)(p.pil0[1] - p.pil0[0]));       // tau_j = angle_j / (2 pi deltak)
         auto q_at = [&](int i) -> double2 { return cmulc(p.pilots_d[i], to_d(Yp[i])); };
-        auto tau_at = [&](int j) -> double { double2 d = cmulc(q_at(j + 1), q_at(j)); return (double)atan2f((float)d.y, (float)d.x) / (2.0 * CUDART_PI * deltak); };
         const int n = M - 1;
-        for (int j = tid; j < n; j += T4_THREADS) taus[j] = tau_at(j);
+        for (int j0 = 0; j0 < n; j0 += T4_THREADS) {          // angle of q_{j+1} conj(q_j): q_j once per thread, q_{j+1} from the next lane
+            const int j = j0 + tid;
+            double2 qa = make_double2(0.0, 0.0), qb;
+            if (j < M) qa = q_at(j);
+            qb.x = __shfl_down_sync(0xffffffffu, qa.x, 1);
+            qb.y = __shfl_down_sync(0xffffffffu, qa.y, 1);
+            if (lane == 31 && j + 1 < M) qb = q_at(j + 1);
+            if (j < n) { const double2 d = cmulc(qb, qa); ang[j] = atan2f((float)d.y, (float)d.x); }
+        }
         __syncthreads();
         const int CH = (n + T4_THREADS - 1) / T4_THREADS;
         const int lo = min(tid * CH, n), hi = min(lo + CH, n);
         int cmask = 0;
-        for (int j = max(lo, 1); j < hi; ++j) { double d = fabs(taus[j] - taus[j - 1]); cmask += (d < 1e-3 && d != 0.0); }
+        for (int j = max(lo, 1); j < hi; ++j) { double d = fabs((double)ang[j] - (double)ang[j - 1]) * inv_c; cmask += (d < 1e-3 && d != 0.0); }   // the difference first: exactly zero for equal angles
         int rank = block_exclusive_scan(cmask, red_i);
         double sum = 0; int kept = 0;
         for (int j = max(lo, 1); j < hi; ++j) {
-            double d = fabs(taus[j] - taus[j - 1]);
-            if (d < 1e-3 && d != 0.0) { if (rank >= p.Np) { sum += taus[j]; ++kept; } ++rank; }
+            const double tj = (double)ang[j] * inv_c, d = fabs((double)ang[j] - (double)ang[j - 1]) * inv_c;
+            if (d < 1e-3 && d != 0.0) { if (rank >= p.Np) { sum += tj; ++kept; } ++rank; }
         }
         sum = block_sum(sum, red);
         double nk = block_sum((double)kept, red);
         tau = sum / nk;
-        double2* prot = (double2*)taus;
+        double2* prot = (double2*)smem_raw;
         __syncthreads();
         for (int q = tid; q < p.Np; q += T4_THREADS) {
             double sn = 0.0, cs = 1.0;
@@ -779,38 +795,50 @@ __global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4Fa
         }
         __syncthreads();
         double ps = 0; int pn = 0;
-        for (int i = tid; i < M; i += T4_THREADS) {
-            const int pq = i % p.Np;
+        for (int i = tid, pq = tid % p.Np; i < M; i += T4_THREADS) {
             double2 rxv = to_d(Yp[i]);
             if (p.time_desync) rxv = cmul(rxv, prot[pq]);
             double2 qq = cmulc(p.pilots_d[i], rxv);
             double a = (double)atan2f((float)qq.y, (float)qq.x);
             if (fabs(a) > 1e-3) { ps += a; ++pn; }
+            pq += step_q; if (pq >= p.Np) pq -= p.Np;
         }
         ps = block_sum(ps, red);
         double pk = block_sum((double)pn, red);
         phase = ps / pk;
         if (tid == 0) { if (tau_out) tau_out[b] = tau; if (phase_out) phase_out[b] = phase; }
     }
-    for (int k = tid; k < p.Nc; k += T4_THREADS) {
-        double sn = 0.0, cs = 1.0;
-        if (p.time_desync || p.freq_desync) {
-            double ang = (p.time_desync ? 2.0 * tau * (double)k : 0.0);
-            double s1, c1, s2 = 0.0, c2 = 1.0;
-            sincospi(ang, &s1, &c1);
-            if (p.freq_desync) sincos(phase, &s2, &c2);
-            cs = c1 * c2 - s1 * s2; sn = s1 * c2 + c1 * s2;
+    {
+        double s2 = 0.0, c2 = 1.0;
+        if (p.freq_desync) sincos(phase, &s2, &c2);
+        for (int k = tid; k < p.Nc; k += T4_THREADS) {
+            double sn = 0.0, cs = 1.0;
+            if (p.time_desync || p.freq_desync) {
+                double s1, c1;
+                sincospi(p.time_desync ? 2.0 * tau * (double)k : 0.0, &s1, &c1);
+                cs = c1 * c2 - s1 * s2; sn = s1 * c2 + c1 * s2;
+            }
+            G[k] = make_float2((float)cs, (float)sn);
         }
-        G[k] = make_float2((float)cs, (float)sn);
     }
     __syncthreads();
     if (p.mp_desync) {
-        for (int q = warp; q < p.Np; q += NW) {
-            float sr = 0.f, si = 0.f;
+        // symbol-averaged pilot LS values: PARTS threads per pilot (consecutive lanes = consecutive pilots: conflict-free shared
+        // reads, coalesced pilot table), partial sums combined in a fixed order
+        const int PARTS = min(min(T4_THREADS / p.Np, 4), p.S);
+        float2* part = (float2*)smem_raw;
+        if (tid < PARTS * p.Np) {
+            const int pt = tid / p.Np, q = tid - pt * p.Np;
             const float2 g = G[p.pil0[q]];
-            for (int s = lane; s < p.S; s += 32) { const float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
-            sr = warp_sum(sr); si = warp_sum(si);
-            if (lane == 0) yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
+            float sr = 0.f, si = 0.f;
+            for (int s = pt; s < p.S; s += PARTS) { const float2 v = cdiv(cmul(Yp[s * p.Np + q], g), p.pilots[(int64_t)s * p.Np + q]); sr += v.x; si += v.y; }
+            part[tid] = make_float2(sr, si);
+        }
+        __syncthreads();
+        for (int q = tid; q < p.Np; q += T4_THREADS) {
+            float sr = 0.f, si = 0.f;
+            for (int pt = 0; pt < PARTS; ++pt) { sr += part[pt * p.Np + q].x; si += part[pt * p.Np + q].y; }
+            yk[q] = make_float2(sr / (float)p.S, si / (float)p.S);
         }
         __syncthreads();
         float2* Hrow = Hout ? Hout + b * p.Nc : nullptr;
@@ -818,49 +846,48 @@ __global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4Fa
             if (Hrow) Hrow[k] = h;
             G[k] = cdiv(G[k], h);
         });
-        __syncthreads();
     }
+    __syncthreads();
+    float2* Gd = Yp;                                             // one-tap equaliser of the data carriers in payload order
+    for (int dr = tid; dr < p.Nd; dr += T4_THREADS) { const int c = p.data0[dr]; Gd[dr] = c < p.Nc ? G[c] : make_float2(0.f, 0.f); }
+    __syncthreads();
     int errs = 0, nears = 0;
-    uint8_t* dec = (uint8_t*)smem_raw;
-    __syncthreads();
-    for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
-        const int cidx = p.data0[dr];
-        const bool in = cidx < p.Nc;
-        const float2 g = in ? G[cidx] : make_float2(0.f, 0.f);
-        const float2* Yc = Ysc + (in ? cidx : 0);
-        for (int s0 = 0; s0 < p.S; s0 += 10) {
-            float2 y[10];
-#pragma unroll
-            for (int u = 0; u < 10; ++u) y[u] = (s0 + u < p.S) ? ldg_stream(Yc + (int64_t)(s0 + u) * p.Nc) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 10; ++u)
-                if (s0 + u < p.S) {
-                    const float2 e = in ? cmul(y[u], g) : make_float2(0.f, 0.f);
-                    float margin = 1.f;
-                    uint32_t code;
-                    if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
-                    else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
-                    if (NEAR && margin < near_eps) ++nears;
-                    dec[(s0 + u) * p.Nd + dr] = (uint8_t)code;
-                }
-        }
-    }
-    __syncthreads();
-    if (QAM16 && (stream_bits & 31) == 0 && p.frame_bits >= 64) {     // word-aligned streams: see rx_t4_fast_kernel
+    if (QAM16 && (stream_bits & 31) == 0 && p.frame_bits >= 64 && (p.Nd & 3) == 0) {
+        // word-aligned 16QAM streams: one thread decides the eight consecutive payload symbols of a 32-bit word (64 contiguous
+        // bytes of the compact data-carrier array); a group of four never straddles two OFDM symbols because Nd % 4 == 0
         const int words = (int)(stream_bits >> 5);
-        auto raw_word = [&](int w) -> uint32_t {
-            const uint2 by = *reinterpret_cast<const uint2*>(dec + 8 * w);
-            uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
-            uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
-            return lo | (hi << 16);
-        };
+        uint32_t* rawW = (uint32_t*)smem_raw;
+        const float4* Yv = reinterpret_cast<const float4*>(Yd);
+        for (int w = tid; w < words; w += T4_THREADS) {
+            float4 y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) y[u] = __ldg(Yv + 4 * w + u);
+            const int i0 = 8 * w;
+            const int dr0 = i0 - (i0 / p.Nd) * p.Nd;
+            const int dr1 = dr0 + 4 >= p.Nd ? 0 : dr0 + 4;
+            float4 g[4];
+            g[0] = *reinterpret_cast<const float4*>(Gd + dr0); g[1] = *reinterpret_cast<const float4*>(Gd + dr0 + 2);
+            g[2] = *reinterpret_cast<const float4*>(Gd + dr1); g[3] = *reinterpret_cast<const float4*>(Gd + dr1 + 2);
+            uint32_t R = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 e0 = cmul(make_float2(y[u].x, y[u].y), make_float2(g[u].x, g[u].y));
+                const float2 e1 = cmul(make_float2(y[u].z, y[u].w), make_float2(g[u].z, g[u].w));
+                float m0 = 1.f, m1 = 1.f;
+                R |= demap16_nib<NEAR>(e0.x, e0.y, fx.two_a, &m0) << (8 * u);
+                R |= demap16_nib<NEAR>(e1.x, e1.y, fx.two_a, &m1) << (8 * u + 4);
+                if (NEAR) nears += (m0 < near_eps) + (m1 < near_eps);
+            }
+            rawW[w] = R;
+        }
+        __syncthreads();
         const uint32_t* tb = txbits ? txbits + b * words : nullptr;
         uint32_t* ob = outbits ? outbits + b * words : nullptr;
         for (int w = tid; w < words; w += T4_THREADS) {
-            const uint32_t R = raw_word(w);
+            const uint32_t R = rawW[w];
             uint32_t o = R;
             if (p.scramble) {
-                const uint32_t P = w ? raw_word(w - 1) : 0u;
+                const uint32_t P = w ? rawW[w - 1] : 0u;
                 const unsigned long long X = ((unsigned long long)R << 32) | P;
                 o = (uint32_t)((X ^ (X << 13) ^ (X << 14)) >> 32);
                 const int fl = (32 * w + 31) / p.frame_bits;
@@ -879,6 +906,28 @@ __global__ void __launch_bounds__(T4_THREADS, 3) t4_post_kernel(T4Params p, T4Fa
             if (ob) ob[w] = o;
         }
     } else {
+        uint8_t* dec = (uint8_t*)smem_raw;
+        for (int dr = tid; dr < p.Nd; dr += T4_THREADS) {
+            const float2 g = Gd[dr];
+            const float2* Yc = Yd + dr;
+            for (int s0 = 0; s0 < p.S; s0 += 10) {
+                float2 y[10];
+#pragma unroll
+                for (int u = 0; u < 10; ++u) y[u] = (s0 + u < p.S) ? ldg_stream(Yc + (int64_t)(s0 + u) * p.Nd) : make_float2(0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 10; ++u)
+                    if (s0 + u < p.S) {
+                        const float2 e = cmul(y[u], g);
+                        float margin = 1.f;
+                        uint32_t code;
+                        if (QAM16) code = demap16_nib<NEAR>(e.x, e.y, fx.two_a, &margin);
+                        else code = (uint32_t)nearest_idx(con, e.x, e.y, &margin);
+                        if (NEAR && margin < near_eps) ++nears;
+                        dec[(s0 + u) * p.Nd + dr] = (uint8_t)code;
+                    }
+            }
+        }
+        __syncthreads();
         const int fpb = p.SpF * p.Nd;
         auto packed = [&](const uint8_t* fr, int wd) -> uint32_t {
             uint32_t word = 0;
@@ -1010,16 +1059,16 @@ extern "C" int ofdm_rx_chain_t4_ex(ofdm_ctx* ctx, const ofdm_link_params* lp, co
                 // large batches: the same arithmetic as three kernels, each at its own occupancy (t4_ifo / t4_sym / t4_post)
                 const int64_t SPLIT_CHUNK = 16384;                      // streams per pass: 2.6 GB of kept bins at the Task-4 shape
                 const bool aligned = stream_bits % 32 == 0;
-                const size_t post_smem = (std::max(taus, (size_t)p.S * p.Nd) + 15) / 16 * 16 + sizeof(float2) * ((size_t)p.S * p.Np + p.Nc + 2 * (size_t)pl->n_knots) + 32;
+                const size_t post_smem = (std::max(std::max(sizeof(float) * (size_t)p.S * p.Np, 16 * (size_t)p.Np), std::max(8 * (size_t)T4_THREADS, (size_t)p.S * p.Nd)) + 15) / 16 * 16 + sizeof(float2) * ((size_t)p.S * p.Np + p.Nc + 2 * (size_t)pl->n_knots) + 32;
                 const size_t sym_smem = tiles + sizeof(float2) * 1024;
-                if (fx.tw_t && B >= 512 && (aligned || B <= SPLIT_CHUNK) && post_smem <= 100 * 1024 && !getenv("OFDM_B200_T4_FUSED")) {
+                if (fx.tw_t && B >= 512 && (aligned || B <= SPLIT_CHUNK) && post_smem <= 100 * 1024 && p.Np <= T4_THREADS && p.Nd <= p.S * p.Np && !getenv("OFDM_B200_T4_FUSED")) {
                     const int64_t CH = std::min<int64_t>(B, SPLIT_CHUNK);
                     const int groups = (p.S + T4_THREADS / 32 - 1) / (T4_THREADS / 32);
                     float2* bins = nullptr;
-                    cudaError_t e = cudaMallocAsync((void**)&bins, sizeof(float2) * (size_t)CH * p.S * ((size_t)p.Nc + p.Np), ctx->stream);
+                    cudaError_t e = cudaMallocAsync((void**)&bins, sizeof(float2) * (size_t)CH * p.S * ((size_t)p.Nd + p.Np), ctx->stream);
                     if (e != cudaSuccess) rc = ctx_fail(ctx, OFDM_ERR_CUDA, "cudaMallocAsync failed: %s", cudaGetErrorString(e));
-                    float2* Ysc_all = bins;
-                    float2* Yp_all = bins + (size_t)CH * p.S * p.Nc;
+                    float2* Yd_all = bins;
+                    float2* Yp_all = bins + (size_t)CH * p.S * p.Nd;
                     int32_t* ifo_ptr = ifo_dev ? ifo_dev : tg_s + B;      // the scratch holds two int32 per stream
                     if (rc == OFDM_OK && !freq_desync && ifo_dev) cudaMemsetAsync(ifo_dev, 0, sizeof(int32_t) * B, ctx->stream);
                     typedef void (*post_t)(T4Params, T4FastExtra, PlanDev<float>, DevConst<float>, int64_t, const float2*, const float2*, const uint32_t*, int64_t,
@@ -1030,6 +1079,8 @@ extern "C" int ofdm_rx_chain_t4_ex(ofdm_ctx* ctx, const ofdm_link_params* lp, co
                     cudaFuncSetAttribute(symk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sym_smem);
                     cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem);
                     const int64_t words = stream_bits / 32;
+                    // (Running the post kernel of one chunk on a side stream under the symbol kernel of the next was tried: the symbol
+                    // kernel's two CTAs hold every register of an SM, nothing co-resides, and the smaller chunks only add tails.)
                     for (int64_t c0 = 0; c0 < B && rc == OFDM_OK; c0 += CH) {
                         const int64_t nb = std::min(CH, B - c0);
                         const float2* rxc = (const float2*)rx + c0 * L;
@@ -1037,8 +1088,8 @@ extern "C" int ofdm_rx_chain_t4_ex(ofdm_ctx* ctx, const ofdm_link_params* lp, co
                             t4_ifo_kernel<<<(unsigned)cdiv64(nb, T4_THREADS / 32), T4_THREADS, tiles, ctx->stream>>>(fx, rxc, nb, L, p.Tg, time_desync, tg_dev + c0, fo_dev + c0, ifo_ptr + c0);
                             ctx->launches++;
                         }
-                        symk<<<(unsigned)(nb * groups), T4_THREADS, sym_smem, ctx->stream>>>(p, fx, rxc, nb, L, groups, tg_dev + c0, fo_dev + c0, ifo_ptr + c0, Ysc_all, Yp_all);
-                        post<<<(unsigned)nb, T4_THREADS, post_smem, ctx->stream>>>(p, fx, plan_dev<float>(pl), make_devconst<float>(lp->constellation), nb, Ysc_all, Yp_all,
+                        symk<<<(unsigned)(nb * groups), T4_THREADS, sym_smem, ctx->stream>>>(p, fx, rxc, nb, L, groups, tg_dev + c0, fo_dev + c0, ifo_ptr + c0, Yd_all, Yp_all);
+                        post<<<(unsigned)nb, T4_THREADS, post_smem, ctx->stream>>>(p, fx, plan_dev<float>(pl), make_devconst<float>(lp->constellation), nb, Yd_all, Yp_all,
                                                                                    tx_bits ? tx_bits + c0 * words : nullptr, nb * stream_bits,
                                                                                    out_bits ? out_bits + c0 * words : nullptr, (unsigned long long*)counts,
                                                                                    tau_dev ? tau_dev + c0 : nullptr, phase_dev ? phase_dev + c0 : nullptr,
