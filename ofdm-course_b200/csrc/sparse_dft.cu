@@ -14,9 +14,11 @@
 // The argmax is taken on FP32 values of alpha; frames whose best two |alpha|^2 differ by less than tie_eps (relative) are
 // counted per frame in near_ties (their tap ORDER may differ from a float64 evaluation).
 #include "pursuit_common.cuh"
+#include "fft_reg.cuh"
 
 #define OD_THREADS 256
 #define OD_EPT 16            // dictionary columns per thread: Ldict <= 4096
+#define OD_NP_S 256          // measurements staged in shared memory up to this many pilots
 #define OD_MAXK 16
 
 // g[d] = sum_i exp(+2*pi*1j*p_i*d/N) = sum_i conj(W_N^{(p_i d) mod N}) from the double twiddle table (exact argument reduction)
@@ -65,6 +67,49 @@ __device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
     return r;
 }
 
+// Unnormalised inverse 4096-point FFT of fa (natural order) for a 256-thread block: three radix-16 Stockham passes with the
+// register butterflies of fft_reg.cuh (forward transform of the conjugate, conjugated on the way out).  Pass 3 leaves
+// thread t with the outputs l = t + 256 r in out[r] -- exactly the dictionary columns that thread owns -- so the result never
+// goes back to shared memory.  Pass-1 stores (stride 16) are XOR-swizzled within groups of 16 to stay bank-conflict free;
+// twiddles W^{q t}, q = 4a + b, are formed as W^{b t} W^{4 a t} from six table reads.  fb is scratch.
+__device__ __forceinline__ void od_twiddle16(float2* v, const float2* __restrict__ tw, int t) {
+    const float2 b1 = __ldg(tw + t), b2 = __ldg(tw + 2 * t), b3 = __ldg(tw + 3 * t);
+    const float2 a1 = __ldg(tw + 4 * t), a2 = __ldg(tw + 8 * t), a3 = __ldg(tw + 12 * t);
+    const float2 wb[4] = {make_float2(1.f, 0.f), b1, b2, b3}, wa[4] = {make_float2(1.f, 0.f), a1, a2, a3};
+#pragma unroll
+    for (int q = 1; q < 16; ++q) {
+        const int a = q >> 2, b = q & 3;
+        const float2 w = a == 0 ? wb[b] : (b == 0 ? wa[a] : cmul(wb[b], wa[a]));
+        v[q] = cmul(v[q], w);
+    }
+}
+__device__ __forceinline__ void od_ifft4096(float2* fa, float2* fb, const float2* __restrict__ tw, int tid, float2* out) {
+    float2 v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { const float2 x = fa[tid + 256 * q]; v[q] = make_float2(x.x, -x.y); }
+    fft16(v);                                            // X[r] sits at v[4 (r & 3) + (r >> 2)]
+#pragma unroll
+    for (int r = 0; r < 16; ++r) fb[16 * tid + (r ^ (tid & 15))] = v[4 * (r & 3) + (r >> 2)];
+    __syncthreads();
+    {
+        const int k = tid & 15, sw = (tid >> 4) & 15;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = fb[(tid + 256 * q) ^ sw];
+        od_twiddle16(v, tw, 16 * k);
+        fft16(v);
+        float2* o = fa + 16 * tid - 15 * k;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) o[16 * r] = v[4 * (r & 3) + (r >> 2)];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = fa[tid + 256 * q];
+    od_twiddle16(v, tw, tid);
+    fft16(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { const float2 x = v[4 * (r & 3) + (r >> 2)]; out[r] = make_float2(x.x, -x.y); }
+}
+
 // NG = groups of 256 dictionary columns a thread works on (Ldict <= 256 NG).
 //
 // The re-fit is carried in ORTHOGONALISED form, so that an iteration needs no triangular solve and the correlation is
@@ -92,6 +137,12 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     __shared__ float2 wf[OD_MAXK], xs[OD_MAXK];
     __shared__ int s_nu, s_nsel, s_stop, s_near, s_col, s_new;
     __shared__ double s_rr;                            // ||r_{n-1}||^2
+    // the per-iteration critical path reads only shared memory: measurements, pilot bins and a two-level double twiddle table
+    // W^k = W^{64 (k >> 6)} W^{k & 63} (one double product instead of a gather from the 64 KB global table)
+    __shared__ float2 y_s[OD_NP_S];
+    __shared__ unsigned short p_s[OD_NP_S];
+    __shared__ double2 w_hi[64], w_lo[64];
+    __shared__ double2 gcol_s[OD_MAXK], gam_s[OD_MAXK];
     float2* fa = (float2*)smem_raw;
     float2* fb = fa + Nfft;
     const int64_t f = blockIdx.x;
@@ -103,20 +154,41 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     for (int i = tid; i < Nfft; i += OD_THREADS) fa[i] = make_float2(0.f, 0.f);
     __syncthreads();
     double yy = 0;
-    for (int i = tid; i < Np; i += OD_THREADS) { const float2 v = y[i]; fa[p0[i]] = v; yy += (double)v.x * v.x + (double)v.y * v.y; }
+    const bool staged = Np <= OD_NP_S;
+    for (int i = tid; i < Np; i += OD_THREADS) {
+        const float2 v = y[i];
+        const int pb = p0[i];
+        fa[pb] = v; yy += (double)v.x * v.x + (double)v.y * v.y;
+        if (staged) { y_s[i] = v; p_s[i] = (unsigned short)pb; }
+    }
+    if (tid < 64) { w_hi[tid] = tw_d[(tid * (Nfft >> 6)) & Nmask]; w_lo[tid] = tw_d[tid & Nmask]; }     // Nfft >= 1024: k = (Nfft / 64) a + b, b < Nfft / 64 <= 64
     if (tid == 0) { s_nu = 0; s_nsel = 0; s_stop = 0; s_near = 0; }
     yy = block_sum(yy, red);          // (barriers inside: the scatter is complete)
     if (tid == 0) s_rr = yy;
     __syncthreads();
-    float2* c = block_fft<float, true>(fa, fb, Nfft, logN, tw);
-    float2 a[NG];                     // the running correlation A^H r
+    float2 c16[NG == 16 ? 16 : 1];
+    float2* c = nullptr;
+    if (NG == 16 && Nfft == 4096) od_ifft4096(fa, fb, tw, tid, c16);      // result in registers, in this thread's column order
+    else c = block_fft<float, true>(fa, fb, Nfft, logN, tw);
+    // the running correlation A^H r, real and imaginary parts of two columns (j, j+1) per register pair: the update below is
+    // then four packed FFMA2 per two columns with the tap coefficient as the (hoisted) broadcast operand
+    float2 ar[NG / 2], ai[NG / 2];
 #pragma unroll
-    for (int j = 0; j < NG; ++j) { const int l = tid + OD_THREADS * j; a[j] = l < Ldict ? c[l] : make_float2(0.f, 0.f); }
+    for (int j = 0; j < NG; j += 2) {
+        const int l0 = tid + OD_THREADS * j, l1 = l0 + OD_THREADS;
+        float2 c0, c1;
+        if (NG == 16 && Nfft == 4096) { c0 = c16[NG == 16 ? j : 0]; c1 = c16[NG == 16 ? j + 1 : 0]; }
+        else { c0 = c[l0]; c1 = c[l1 < Nfft ? l1 : l0]; }
+        if (l0 >= Ldict) c0 = make_float2(0.f, 0.f);
+        if (l1 >= Ldict) c1 = make_float2(0.f, 0.f);
+        ar[j / 2] = make_float2(c0.x, c1.x); ai[j / 2] = make_float2(c0.y, c1.y);
+    }
     __syncthreads();
-    // g twice in a row (both FFT buffers are free now): entry (l - c) mod Nfft is read as gS[base + 256 j] with ONE base per
-    // selected tap and immediate offsets, no wrap-around arithmetic in the inner loop
-    float2* gS = fa;
-    for (int i = tid; i < 2 * Nfft; i += OD_THREADS) gS[i] = g_f[i & Nmask];
+    // g twice in a row, real and imaginary planes (both FFT buffers are free now): entry (l - c) mod Nfft is read as
+    // gR[base + 256 j] with ONE base per selected tap and immediate offsets, no wrap-around arithmetic in the inner loop
+    float* gR = (float*)fa;
+    float* gI = gR + 2 * Nfft;
+    for (int i = tid; i < 2 * Nfft; i += OD_THREADS) { const float2 v = g_f[i & Nmask]; gR[i] = v.x; gI[i] = v.y; }
     __syncthreads();
 
     for (int it = 0; it < K; ++it) {
@@ -126,7 +198,8 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
 #pragma unroll
         for (int j = 0; j < NG; ++j) {
             const int l = tid + OD_THREADS * j;
-            const float m = l < Ldict ? a[j].x * a[j].x + a[j].y * a[j].y : -CUDART_INF_F;
+            const float re = (j & 1) ? ar[j / 2].y : ar[j / 2].x, im = (j & 1) ? ai[j / 2].y : ai[j / 2].x;
+            const float m = l < Ldict ? re * re + im * im : -CUDART_INF_F;
             if (m > t.b1) { t.b2 = t.b1; t.b1 = m; t.i1 = l; } else t.b2 = fmaxf(t.b2, m);
         }
 #pragma unroll
@@ -159,16 +232,29 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         __syncthreads();
         const int col = s_col, is_new = s_new;
         if (!is_new) break;               // a column selected twice leaves the residual unchanged: ||r_i - r_{i-1}|| = 0 < 1e-2 (`:20`), it >= 1 always here
+        // G[c_lane][c_n] for the Gram-Schmidt step below: issued now, consumed after the block-wide b_n (hides the global latency)
+        double2 gcol = make_double2(0, 0);
+        if (warp == 0 && lane < nu) gcol = g_d[(ucol[lane] - col) & Nmask];
         {
-            // b_n = conj(a_new) . y in double: one table twiddle per pilot, block-wide
-            double ar = 0, ai = 0;
-            for (int i = tid; i < Np; i += OD_THREADS) {
-                const double2 w = tw_d[(p0[i] * col) & Nmask];             // A(i, col)
-                const float2 v = y[i];
-                ar += w.x * v.x + w.y * v.y; ai += w.x * v.y - w.y * v.x;  // conj(w) * v
+            // b_n = conj(a_new) . y in double, block-wide
+            double ar_ = 0, ai_ = 0;
+            if (staged) {
+                const int qs = logN - 6, qm = (1 << qs) - 1;
+                for (int i = tid; i < Np; i += OD_THREADS) {
+                    const int k = ((int)p_s[i] * col) & Nmask;
+                    const double2 w = cmul(w_hi[k >> qs], w_lo[k & qm]);       // A(i, col)
+                    const float2 v = y_s[i];
+                    ar_ += w.x * v.x + w.y * v.y; ai_ += w.x * v.y - w.y * v.x;  // conj(w) * v
+                }
+            } else {
+                for (int i = tid; i < Np; i += OD_THREADS) {
+                    const double2 w = tw_d[(p0[i] * col) & Nmask];
+                    const float2 v = y[i];
+                    ar_ += w.x * v.x + w.y * v.y; ai_ += w.x * v.y - w.y * v.x;
+                }
             }
-            ar = warp_sum(ar); ai = warp_sum(ai);
-            if (lane == 0) { red[2 * warp] = ar; red[2 * warp + 1] = ai; }
+            ar_ = warp_sum(ar_); ai_ = warp_sum(ai_);
+            if (lane == 0) { red[2 * warp] = ar_; red[2 * warp + 1] = ai_; }
             __syncthreads();
         }
         if (warp == 0) {
@@ -176,25 +262,22 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
             double2 bn = make_double2(0, 0);
             for (int w = 0; w < OD_THREADS / 32; ++w) { bn.x += red[2 * w]; bn.y += red[2 * w + 1]; }
             if (lane == 0) bvec[n] = bn;
-            // gamma_j (lane j < n) = sum_{i<=j} conj(T_ij) G[c_i][c_n] / ||u_j||^2
-            const double2 gcol = lane < n ? g_d[(ucol[lane] - col) & Nmask] : make_double2(0, 0);     // G[c_lane][c_n]
+            // gamma_j (lane j < n) = sum_{i<=j} conj(T_ij) G[c_i][c_n] / ||u_j||^2   (vectors exchanged through shared memory:
+            // independent loads instead of a shuffle per term on the serial path)
+            if (lane < n) gcol_s[lane] = gcol;
+            __syncwarp();
             double2 gam = make_double2(0, 0);
-            for (int i = 0; i < n; ++i) {
-                const double2 gi = make_double2(__shfl_sync(0xffffffffu, gcol.x, i), __shfl_sync(0xffffffffu, gcol.y, i));
-                if (lane < n && i <= lane) gam = gam + cmul(cconj(Tm[i][lane]), gi);
-            }
+            if (lane < n) for (int i = 0; i <= lane; ++i) gam = gam + cmul(cconj(Tm[i][lane]), gcol_s[i]);
             const double u2 = lane < n ? un2[lane] : 1.0;
             gam = (lane < n && u2 > 0) ? cscale(gam, 1.0 / u2) : make_double2(0, 0);
+            if (lane < n) gam_s[lane] = gam;
             // ||u_n||^2 = G_nn - sum_j |gamma_j|^2 ||u_j||^2
             double nn = lane < n ? (gam.x * gam.x + gam.y * gam.y) * u2 : 0.0;
-            nn = warp_sum(nn);
+            nn = warp_sum(nn);                                             // (also orders gam_s)
             const double un = fmax(g_d[0].x - nn, 0.0);
             // T_in (lane i < n) = - sum_{j=i}^{n-1} gamma_j T_ij ; T_nn = 1
             double2 tin = make_double2(0, 0);
-            for (int j = 0; j < n; ++j) {
-                const double2 gj = make_double2(__shfl_sync(0xffffffffu, gam.x, j), __shfl_sync(0xffffffffu, gam.y, j));
-                if (lane < n && j >= lane) tin = tin - cmul(gj, Tm[lane][j]);
-            }
+            if (lane < n) for (int j = lane; j < n; ++j) tin = tin - cmul(gam_s[j], Tm[lane][j]);
             if (lane == n) tin = make_double2(1, 0);
             if (lane <= n) Tm[lane][n] = tin;
             // beta_n = sum_{i<=n} conj(T_in) b_i / ||u_n||^2
@@ -217,14 +300,19 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         // ---- alpha -= sum_{i<=n} (beta_n T_in) g[(l - c_i) mod N]
         // (two packed FFMA2 per column: the table value is the broadcast operand, -w and its rotation are hoisted per tap)
         for (int q = 0; q <= nu; ++q) {
-            const float2 x = wf[q];
-            const float2 w0 = make_float2(-x.x, -x.y), w1 = make_float2(x.y, -x.x);      // a -= g*x = g.x*(-x) + g.y*(-i x)... (x.y, -x.x) = -i*x negated
-            const float2* gp = gS + ((tid - ucol[q]) & Nmask);
+            const float2 x = wf[q];                                                        // a -= g x:  re -= gr xr - gi xi,  im -= gr xi + gi xr
+            const float2 nxr = make_float2(-x.x, -x.x), pxi = make_float2(x.y, x.y), nxi = make_float2(-x.y, -x.y);
+            const int base = (tid - ucol[q]) & Nmask;
+            const float* gr = gR + base;
+            const float* gi = gI + base;
 #pragma unroll
-            for (int j = 0; j < NG; ++j) {
-                const float2 gv = gp[OD_THREADS * j];
-                a[j] = __ffma2_rn(make_float2(gv.x, gv.x), w0, a[j]);
-                a[j] = __ffma2_rn(make_float2(gv.y, gv.y), w1, a[j]);
+            for (int j = 0; j < NG; j += 2) {
+                const float2 g_r = make_float2(gr[OD_THREADS * j], gr[OD_THREADS * (j + 1)]);
+                const float2 g_i = make_float2(gi[OD_THREADS * j], gi[OD_THREADS * (j + 1)]);
+                ar[j / 2] = __ffma2_rn(g_r, nxr, ar[j / 2]);
+                ar[j / 2] = __ffma2_rn(g_i, pxi, ar[j / 2]);
+                ai[j / 2] = __ffma2_rn(g_r, nxi, ai[j / 2]);
+                ai[j / 2] = __ffma2_rn(g_i, nxr, ai[j / 2]);
             }
         }
     }
@@ -250,11 +338,10 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     __syncthreads();
     if (hout) {
         float2* hb = hout + f * (int64_t)Nfft;
-        for (int i = tid; i < Nfft; i += OD_THREADS) {
-            float2 v = make_float2(0.f, 0.f);
-            for (int u = 0; u < nu; ++u) if (ucol[u] == i) v = hval[u];
-            hb[i] = v;
-        }
+        float4* hb4 = reinterpret_cast<float4*>(hb);
+        for (int i = tid; i < Nfft / 2; i += OD_THREADS) hb4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();                                  // the zeros of this block are ordered before its nu taps
+        if (tid < nu) hb[ucol[tid]] = hval[tid];
     }
     if (Hout) {
         // H(m) = sum_u h_u W^{c_u m}; with m = 64 a + b the twiddle is W^{64 c a} * W^{c b}: two 64-entry rows per tap
@@ -268,15 +355,24 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
             t_lo[e] = tw[(j * ucol[u]) & Nmask];
         }
         __syncthreads();
-        for (int mm = tid; mm < Nfft; mm += OD_THREADS) {
-            const int aa = mm >> 6, bq = mm & 63;
-            float2 acc = make_float2(0.f, 0.f);
+        // thread tid owns m = tid + 256 j: b = tid & 63 is fixed (one low twiddle per tap), a = (tid >> 6) + 4 j; NG values of j at a time
+        const int bq = tid & 63, a0 = tid >> 6;
+        for (int j0 = 0; OD_THREADS * j0 < Nfft; j0 += NG) {
+            float2 acc[NG];
+#pragma unroll
+            for (int j = 0; j < NG; ++j) acc[j] = make_float2(0.f, 0.f);
             for (int u = 0; u < nu; ++u) {
-                const float2 x = t_hi[64 * u + aa], w = t_lo[64 * u + bq];
-                acc = __ffma2_rn(make_float2(x.x, x.x), w, acc);                        // x * w, x the broadcast operand
-                acc = __ffma2_rn(make_float2(x.y, x.y), make_float2(-w.y, w.x), acc);
+                const float2 w = t_lo[64 * u + bq], wr = make_float2(-w.y, w.x);
+                const float2* th = t_hi + 64 * u + a0 + (OD_THREADS / 64) * j0;
+#pragma unroll
+                for (int j = 0; j < NG; ++j) {
+                    const float2 x = th[(OD_THREADS / 64) * j];
+                    acc[j] = __ffma2_rn(make_float2(x.x, x.x), w, acc[j]);              // x * w, x the broadcast operand
+                    acc[j] = __ffma2_rn(make_float2(x.y, x.y), wr, acc[j]);
+                }
             }
-            Hout[f * (int64_t)Nfft + mm] = acc;
+#pragma unroll
+            for (int j = 0; j < NG; ++j) { const int mm = tid + OD_THREADS * (j0 + j); if (mm < Nfft) Hout[f * (int64_t)Nfft + mm] = acc[j]; }
         }
     }
 }

@@ -38,3 +38,22 @@ w = ctx.window_papr(tx.reshape(B, -1)[:, :3 * 4608].contiguous(), 4096)
 xs, cc = ctx.ccdf(w.reshape(-1)[:5000].contiguous())
 ctx.sync()
 print("T5 counts", r5["counts"].cpu().numpy(), "T4 counts", r4["counts"].cpu().numpy(), "papr windows", tuple(w.shape), "ccdf points", xs.numel())
+if os.environ.get("SAN_BIG"):
+    # persistent loops of the three-CTA rx4096 kernel (more streams than CTAs), the split Task-4 chain (>= 512 streams),
+    # the sweep entry point and the Batch-OMP kernel
+    from ofdm_b200 import layouts
+    B5 = 460                                             # > 3 x 148 CTAs: some CTAs walk on to a second stream
+    lp5 = layouts.task5_link(ctx, comb=4)
+    bits5 = torch.randint(-2**31, 2**31 - 1, (B5 * lp5.stream_bits // 32,), dtype=torch.int32, device=ctx.device)
+    tx5, ps5 = ctx.tx_chain(lp5, bits5, B5, want_power=True)
+    rx5 = ctx.channel_t5(tx5, snr_db=15.0, h_dev=ctx.cplx(h), seed=3, power_sum=ps5)
+    big5 = ctx.rx_chain_t5(lp5, rx5, B5, tx_bits_dev=bits5, near_eps=1e-4, want_bits=False, want_H=False)
+    Bs = 512
+    rx4b = ctx.cplx(np.tile(np.stack(rx4), (Bs // 2, 1)))
+    b4b = ctx.bits(np.tile(b4, (Bs // 2, 1)).ravel())
+    big4 = ctx.rx_chain_t4_fused(lp4, rx4b, tx_bits_dev=b4b, near_eps=1e-3, want_H=True)
+    pil = np.sort(rng.permutation(1024)[:64]) + 1
+    yo = (torch.randn(8, 64, device=ctx.device) + 1j * torch.randn(8, 64, device=ctx.device)).to(torch.complex64)
+    om = ctx.omp(yo, 1024, 5, Ldict=1024, pilot_loc=pil)
+    ctx.sync()
+    print("big T5", big5["counts"].cpu().numpy(), "big T4", big4["counts"].cpu().numpy(), "omp", type(om).__name__)
