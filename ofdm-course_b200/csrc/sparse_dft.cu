@@ -110,6 +110,15 @@ __device__ __forceinline__ void od_ifft4096(float2* fa, float2* fb, const float2
     for (int r = 0; r < 16; ++r) { const float2 x = v[4 * (r & 3) + (r >> 2)]; out[r] = make_float2(x.x, -x.y); }
 }
 
+// Warp-wide top-2 of unsigned keys: on return every lane holds the largest key, the smallest index that carries it and the
+// largest key among all other candidates (each lane contributes its own runner-up k2 as well).
+__device__ __forceinline__ void od_top2_redux(unsigned& k1, int& i1, unsigned& k2) {
+    const unsigned K1 = __reduce_max_sync(0xffffffffu, k1);
+    const int I1 = (int)__reduce_min_sync(0xffffffffu, k1 == K1 ? (unsigned)i1 : 0x7fffffffu);
+    const unsigned K2 = __reduce_max_sync(0xffffffffu, (k1 == K1 && i1 == I1) ? k2 : k1);
+    k1 = K1; i1 = I1; k2 = K2;
+}
+
 // NG = groups of 256 dictionary columns a thread works on (Ldict <= 256 NG).
 //
 // The re-fit is carried in ORTHOGONALISED form, so that an iteration needs no triangular solve and the correlation is
@@ -133,9 +142,9 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     __shared__ int sel[OD_MAXK], ucol[OD_MAXK];
     __shared__ double2 Tm[OD_MAXK][OD_MAXK + 1];      // T[i][n], i <= n
     __shared__ double2 bvec[OD_MAXK], beta[OD_MAXK];
-    __shared__ double un2[OD_MAXK];                    // ||u_j||^2
+    __shared__ double un2[OD_MAXK], iun2[OD_MAXK];    // ||u_j||^2 and its reciprocal
     __shared__ float2 wf[OD_MAXK], xs[OD_MAXK];
-    __shared__ int s_nu, s_nsel, s_stop, s_near, s_col, s_new;
+    __shared__ int s_stop;
     __shared__ double s_rr;                            // ||r_{n-1}||^2
     // the per-iteration critical path reads only shared memory: measurements, pilot bins and a two-level double twiddle table
     // W^k = W^{64 (k >> 6)} W^{k & 63} (one double product instead of a gather from the 64 KB global table)
@@ -162,7 +171,7 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         if (staged) { y_s[i] = v; p_s[i] = (unsigned short)pb; }
     }
     if (tid < 64) { w_hi[tid] = tw_d[(tid * (Nfft >> 6)) & Nmask]; w_lo[tid] = tw_d[tid & Nmask]; }     // Nfft >= 1024: k = (Nfft / 64) a + b, b < Nfft / 64 <= 64
-    if (tid == 0) { s_nu = 0; s_nsel = 0; s_stop = 0; s_near = 0; }
+    if (tid == 0) s_stop = 0;
     yy = block_sum(yy, red);          // (barriers inside: the scatter is complete)
     if (tid == 0) s_rr = yy;
     __syncthreads();
@@ -191,46 +200,48 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     for (int i = tid; i < 2 * Nfft; i += OD_THREADS) { const float2 v = g_f[i & Nmask]; gR[i] = v.x; gI[i] = v.y; }
     __syncthreads();
 
+    int nu = 0, nsel = 0, near_cnt = 0;                  // block-uniform bookkeeping, carried in registers by every thread
+    const bool full_dict = Ldict == OD_THREADS * NG;
+    const double g0 = g_d[0].x;                          // ||a_l||^2, the same for every column
     for (int it = 0; it < K; ++it) {
-        const int nu = s_nu, nsel = s_nsel;
-        // ---- first maximum of |A^H r|^2 and the runner-up, one fused block reduction (`OMP_estimate.m:7,14`)
+        // ---- first maximum of |A^H r|^2 and the runner-up (`OMP_estimate.m:7,14`).  Per thread: a top-2 scan of its columns in
+        // floating point (a NaN never wins a '>').  Across lanes and warps: |.|^2 >= 0, so the IEEE bit pattern + 1 is an
+        // order-preserving unsigned key (0 = nothing valid) and each level is three warp-wide REDUX instructions -- largest
+        // key, smallest index holding it, largest key among the rest -- instead of five shuffle-and-merge rounds.
         Top2 t; t.b1 = -CUDART_INF_F; t.i1 = 0x7fffffff; t.b2 = -CUDART_INF_F;
+        if (full_dict) {
 #pragma unroll
-        for (int j = 0; j < NG; ++j) {
-            const int l = tid + OD_THREADS * j;
-            const float re = (j & 1) ? ar[j / 2].y : ar[j / 2].x, im = (j & 1) ? ai[j / 2].y : ai[j / 2].x;
-            const float m = l < Ldict ? re * re + im * im : -CUDART_INF_F;
-            if (m > t.b1) { t.b2 = t.b1; t.b1 = m; t.i1 = l; } else t.b2 = fmaxf(t.b2, m);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            Top2 u;
-            u.b1 = __shfl_xor_sync(0xffffffffu, t.b1, o); u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o); u.b2 = __shfl_xor_sync(0xffffffffu, t.b2, o);
-            t = top2_merge(t, u);
-        }
-        if (lane == 0) stop2[warp] = t;
-        __syncthreads();
-        if (warp == 0) {
-            t = lane < OD_THREADS / 32 ? stop2[lane] : Top2{-CUDART_INF_F, 0x7fffffff, -CUDART_INF_F};
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                Top2 u;
-                u.b1 = __shfl_xor_sync(0xffffffffu, t.b1, o); u.i1 = __shfl_xor_sync(0xffffffffu, t.i1, o); u.b2 = __shfl_xor_sync(0xffffffffu, t.b2, o);
-                t = top2_merge(t, u);
+            for (int j = 0; j < NG; ++j) {
+                const float re = (j & 1) ? ar[j / 2].y : ar[j / 2].x, im = (j & 1) ? ai[j / 2].y : ai[j / 2].x;
+                const float m = re * re + im * im;
+                if (m > t.b1) { t.b2 = t.b1; t.b1 = m; t.i1 = tid + OD_THREADS * j; } else t.b2 = fmaxf(t.b2, m);
             }
-            if (lane == 0) {
-                const int col = (t.i1 == 0x7fffffff) ? 0 : t.i1;          // all-NaN correlation: MATLAB's max returns index 1
-                if (!(t.b1 - t.b2 > tie_eps * t.b1)) s_near += 1;
-                int slot = -1;
-                for (int q = 0; q < nu; ++q) if (ucol[q] == col) slot = q;
-                sel[nsel] = col;
-                if (slot < 0) { ucol[nu] = col; s_new = 1; s_nu = nu + 1; } else s_new = 0;
-                s_nsel = nsel + 1;
-                s_col = col;
+        } else {
+#pragma unroll
+            for (int j = 0; j < NG; ++j) {
+                const int l = tid + OD_THREADS * j;
+                const float re = (j & 1) ? ar[j / 2].y : ar[j / 2].x, im = (j & 1) ? ai[j / 2].y : ai[j / 2].x;
+                const float m = l < Ldict ? re * re + im * im : -CUDART_INF_F;
+                if (m > t.b1) { t.b2 = t.b1; t.b1 = m; t.i1 = l; } else t.b2 = fmaxf(t.b2, m);
             }
         }
+        unsigned k1 = t.b1 >= 0.f ? __float_as_uint(t.b1) + 1u : 0u, k2 = t.b2 >= 0.f ? __float_as_uint(t.b2) + 1u : 0u;
+        int i1 = t.i1;
+        od_top2_redux(k1, i1, k2);
+        if (lane == 0) { stop2[warp].b1 = __uint_as_float(k1); stop2[warp].i1 = i1; stop2[warp].b2 = __uint_as_float(k2); }   // keys, bit-cast
         __syncthreads();
-        const int col = s_col, is_new = s_new;
+        // every warp merges the eight warp results itself (same answer): no warp-0 section, no second barrier
+        static_assert(OD_THREADS / 32 == 8, "the final merge assumes eight warps");
+        k1 = lane < 8 ? __float_as_uint(stop2[lane & 7].b1) : 0u;
+        k2 = lane < 8 ? __float_as_uint(stop2[lane & 7].b2) : 0u;
+        i1 = lane < 8 ? stop2[lane & 7].i1 : 0x7fffffff;
+        od_top2_redux(k1, i1, k2);
+        t.b1 = k1 ? __uint_as_float(k1 - 1u) : -CUDART_INF_F; t.b2 = k2 ? __uint_as_float(k2 - 1u) : -CUDART_INF_F; t.i1 = k1 ? i1 : 0x7fffffff;
+        const int col = (t.i1 == 0x7fffffff) ? 0 : t.i1;                  // all-NaN correlation: MATLAB's max returns index 1
+        if (!(t.b1 - t.b2 > tie_eps * t.b1)) ++near_cnt;
+        const int is_new = __ballot_sync(0xffffffffu, lane < nu && ucol[lane] == col) == 0u;
+        if (tid == 0) { sel[nsel] = col; if (is_new) ucol[nu] = col; }     // (readers of the new entry are behind the next barrier)
+        ++nsel;
         if (!is_new) break;               // a column selected twice leaves the residual unchanged: ||r_i - r_{i-1}|| = 0 < 1e-2 (`:20`), it >= 1 always here
         // G[c_lane][c_n] for the Gram-Schmidt step below: issued now, consumed after the block-wide b_n (hides the global latency)
         double2 gcol = make_double2(0, 0);
@@ -269,37 +280,40 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
             double2 gam = make_double2(0, 0);
             if (lane < n) for (int i = 0; i <= lane; ++i) gam = gam + cmul(cconj(Tm[i][lane]), gcol_s[i]);
             const double u2 = lane < n ? un2[lane] : 1.0;
-            gam = (lane < n && u2 > 0) ? cscale(gam, 1.0 / u2) : make_double2(0, 0);
+            gam = (lane < n && u2 > 0) ? cscale(gam, iun2[lane]) : make_double2(0, 0);       // iun2 = 1 / ||u_j||^2, kept from iteration j
             if (lane < n) gam_s[lane] = gam;
-            // ||u_n||^2 = G_nn - sum_j |gamma_j|^2 ||u_j||^2
-            double nn = lane < n ? (gam.x * gam.x + gam.y * gam.y) * u2 : 0.0;
-            nn = warp_sum(nn);                                             // (also orders gam_s)
-            const double un = fmax(g_d[0].x - nn, 0.0);
+            __syncwarp();
             // T_in (lane i < n) = - sum_{j=i}^{n-1} gamma_j T_ij ; T_nn = 1
             double2 tin = make_double2(0, 0);
             if (lane < n) for (int j = lane; j < n; ++j) tin = tin - cmul(gam_s[j], Tm[lane][j]);
             if (lane == n) tin = make_double2(1, 0);
             if (lane <= n) Tm[lane][n] = tin;
-            // beta_n = sum_{i<=n} conj(T_in) b_i / ||u_n||^2
+            // ||u_n||^2 = G_nn - sum_j |gamma_j|^2 ||u_j||^2 ;  beta_n = sum_{i<=n} conj(T_in) b_i / ||u_n||^2
+            // (the three warp sums are independent: their shuffle chains overlap)
+            double nn = lane < n ? (gam.x * gam.x + gam.y * gam.y) * u2 : 0.0;
             double2 part = make_double2(0, 0);
             if (lane < n) part = cmul(cconj(tin), bvec[lane]);
             else if (lane == n) part = bn;
-            part.x = warp_sum(part.x); part.y = warp_sum(part.y);
-            const double2 bt = un > 0 ? cscale(part, 1.0 / un) : make_double2(0, 0);
-            if (lane == 0) { un2[n] = un; beta[n] = bt; }
+            nn = warp_sum(nn); part.x = warp_sum(part.x); part.y = warp_sum(part.y);
+            const double un = fmax(g0 - nn, 0.0);
+            const double iun = un > 0 ? 1.0 / un : 0.0;
+            const double2 bt = cscale(part, iun);
+            if (lane == 0) { un2[n] = un; iun2[n] = iun; beta[n] = bt; }
             if (lane <= n) { const double2 w = cmul(bt, tin); wf[lane] = make_float2((float)w.x, (float)w.y); }
-            // stopping rule: ||r_n - r_{n-1}|| / ||r_{n-1}|| < 1e-2 from the second selection on
+            // stopping rule: ||r_n - r_{n-1}|| / ||r_{n-1}|| < 1e-2 from the second selection on, compared squared
+            // (dn < 1e-4 on: no square roots or division on the serial path; on = 0 never stops, as the quotient form)
             if (lane == 0) {
                 const double dn = (bt.x * bt.x + bt.y * bt.y) * un, on = s_rr;
-                if (it >= 1 && sqrt(fmax(dn, 0.0)) / sqrt(fmax(on, 0.0)) < 1e-2) s_stop = 1;
+                if (it >= 1 && fmax(dn, 0.0) < 1e-4 * fmax(on, 0.0)) s_stop = 1;
                 s_rr = on - dn;
             }
         }
         __syncthreads();
+        ++nu;                             // the new column is in
         if (s_stop || it == K - 1) break;
         // ---- alpha -= sum_{i<=n} (beta_n T_in) g[(l - c_i) mod N]
-        // (two packed FFMA2 per column: the table value is the broadcast operand, -w and its rotation are hoisted per tap)
-        for (int q = 0; q <= nu; ++q) {
+        // (four packed FFMA2 per two columns: the tap coefficient is the hoisted broadcast operand)
+        for (int q = 0; q < nu; ++q) {
             const float2 x = wf[q];                                                        // a -= g x:  re -= gr xr - gi xi,  im -= gr xi + gi xr
             const float2 nxr = make_float2(-x.x, -x.x), pxi = make_float2(x.y, x.y), nxi = make_float2(-x.y, -x.y);
             const int base = (tid - ucol[q]) & Nmask;
@@ -318,7 +332,6 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
     }
     __syncthreads();
     // ---- gains x = T beta on the unique columns; a repeated last column shares its unknown (pinv's minimum-norm split)
-    const int nsel = s_nsel, nu = s_nu;
     __shared__ float2 hval[OD_MAXK];
     if (warp == 0) {
         double2 xv = make_double2(0, 0);
@@ -332,7 +345,7 @@ __global__ void __launch_bounds__(OD_THREADS, 3) omp_dft_kernel(const float2* __
         if (lane == 0) {
             if (index_out) for (int q = 0; q < K; ++q) index_out[f * K + q] = q < nsel ? sel[q] + 1 : 0;
             if (iters_out) iters_out[f] = nsel;
-            if (near_out) near_out[f] = s_near;
+            if (near_out) near_out[f] = near_cnt;
         }
     }
     __syncthreads();
