@@ -268,6 +268,13 @@ OFDM_API int ofdm_channel_t5(ofdm_ctx*, const void* tx_dev, int64_t B, int64_t L
 OFDM_API int ofdm_channel_t5_p(ofdm_ctx*, const void* tx_dev, int64_t B, int64_t L, const double* snr_db_dev,
                                const double* power_sum_dev, const void* normals_dev, uint64_t seed, int64_t first_stream_id,
                                const void* h_dev, int D, void* rx_dev);
+/* Task-4 channel in one pass (`Task 4/Main_model_Task_4.m:95,103,110,263-264`): Noise -> add_STO(nsto) -> add_CFO(cfo) ->
+ * multipath FIR; bit-identical to ofdm_add_noise -> ofdm_add_sto -> ofdm_add_cfo -> ofdm_apply_fir on the same arguments
+ * (nsto_dev B int32 and cfo_dev B doubles as those calls take them; power_sum_dev may be NULL; h_dev D <= 1024 samples,
+ * a single 1 for "no multipath"). */
+OFDM_API int ofdm_channel_t4_p(ofdm_ctx*, const void* tx_dev, int64_t B, int64_t L, const double* snr_db_dev,
+                               const double* power_sum_dev, const void* normals_dev, uint64_t seed, int64_t first_stream_id,
+                               const int32_t* nsto_dev, const double* cfo_dev, int Nfft, const void* h_dev, int D, void* rx_dev);
 /* M1 RX chain: OFDM_demodulator -> LS_CE -> equalize_signal -> get_payload -> demapping ->
  * DeScrambler -> BER count, one pass over the stream (`Task 5/Task5_part2.m:169-174,269-303`).
  * rx_dev B x S x (Nfft+Tg); tx_bits_dev reference bits (B x stream_bits); outputs (each optional):

@@ -89,6 +89,7 @@ SIGNATURES = {
     "ofdm_tx_chain_p": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp]),
     "ofdm_channel_t5_p": (i32, [vp, vp, i64, i64, vp, vp, vp, u64, i64, vp, i32, vp]),
     "ofdm_channel_t5": (i32, [vp, vp, i64, i64, vp, vp, u64, i64, vp, i32, vp]),
+    "ofdm_channel_t4_p": (i32, [vp, vp, i64, i64, vp, vp, vp, u64, i64, vp, vp, i32, vp, i32, vp]),
     "ofdm_rx_chain_t5": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, vp, dbl]),
     "ofdm_rx_chain_t5_host": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, i64]),
     "ofdm_rx_chain_t5_host_eps": (i32, [vp, C.POINTER(LinkParams), vp, i64, vp, vp, vp, vp, i64, dbl]),

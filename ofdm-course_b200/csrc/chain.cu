@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
 }
 
 int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* power_sum);   // channel.cu
+int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, bool* handled);   // chain_rx_t4.cu
 extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time) {
     return ofdm_tx_chain_p(ctx, lp, bits, B, time, nullptr);
 }
@@ -338,6 +339,17 @@ extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const 
             LAUNCH_CHECK(ctx);
             return OFDM_OK;
         }
+    }
+    {
+        LinkDev<float> chk;                               // (argument validation is the generic path's)
+        bool fast = false;
+        if (ctx->precision == OFDM_PREC_F32 && lp && lp->Nfft == 1024) {
+            int rc = make_linkdev<float>(ctx, lp, chk);
+            if (rc) return rc;
+            rc = ofdm_tx1024_fast(ctx, lp, bits, B, time, &fast);
+            if (rc) return rc;
+        }
+        if (fast) return power ? ofdm_stream_power_sum(ctx, time, B, (int64_t)lp->S * (lp->Nfft + lp->Tg), power) : OFDM_OK;
     }
     DISPATCH_T(ctx, {
         LinkDev<T> d;

@@ -971,6 +971,139 @@ __global__ void __launch_bounds__(T4_THREADS, 4) t4_post_kernel(T4Params p, T4Fa
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TX side of the Task-4 shape (Nfft = 1024), same structure as t4_sym_kernel run backwards: one CTA per stream scrambles all
+// of its frames at once in shared memory (log-depth GF(2) products, as tx_chain_kernel), then ONE WARP builds and transforms
+// a symbol: lane m2 forms the (conjugated) carriers 32 m1 + m2 straight from the frame's bit array, DFT over m1 in
+// registers, twiddle, 32 x 33 transpose, DFT over m2; lane j1 then holds the samples n = j1 + 32 j2, every store is a
+// 256-byte row, rows j2 >= (1024 - Tg) / 32 are written a second time as the cyclic prefix (`OFDM_modulator.m:5-9`).
+// ifft(X) = conj(fft(conj(X))) / N.  Replaces scrambler / mapping / OFDM_map_carriers / OFDM_modulator for this shape.
+struct Tx1024Params {
+    int Tg, Nc, S, SpF, Nd, Np, bps, scramble, frame_bits, frames, m1n;
+    uint32_t prev0;
+    const int32_t* slot;       // 1024: data rank / -1-pilot / SLOT_ZERO
+    const float2* pilots;      // Np x S column-major
+    const float2* tw_t;
+};
+#define T4_SLOT_ZERO (-2147483647 - 1)
+__device__ __forceinline__ uint32_t t4_sm_get32(const uint32_t* w, int pos, int nwords) {     // 32 bits from bit `pos` of a frame array; outside reads 0
+    if (pos < 0) return pos <= -32 ? 0u : w[0] << (-pos);
+    const int wi = pos >> 5, sh = pos & 31;
+    const uint32_t lo = wi < nwords ? w[wi] : 0u;
+    const uint32_t hi = (sh && wi + 1 < nwords) ? w[wi + 1] : 0u;
+    return __funnelshift_r(lo, hi, sh);
+}
+__global__ void __launch_bounds__(T4_THREADS, 2) tx1024_kernel(Tx1024Params p, DevConst<float> con, const uint32_t* __restrict__ bits, int64_t total_bits,
+                                                               float2* __restrict__ out) {
+    constexpr int N = 1024;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = T4_THREADS / 32;
+    float2* tiles = (float2*)smem_raw;
+    const int fw = (p.frame_bits + 31) >> 5;
+    uint32_t* s0 = (uint32_t*)(tiles + NW * 32 * T4F_EROW);
+    uint32_t* s1 = s0 + p.frames * fw;
+    __shared__ float2 cs[16];                                  // conjugated constellation
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.x;
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    if (tid < 16) cs[tid] = make_float2(con.re[tid], -con.im[tid]);
+    for (int i = tid; i < p.frames * fw; i += T4_THREADS) {
+        const int f = i / fw, w = i - f * fw;
+        const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
+        uint32_t v = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+        if (w == 0 && p.scramble) v ^= (p.prev0 >> 19) ^ (p.prev0 >> 18);     // fold the register pre-history into the input
+        s0[i] = v;
+    }
+    __syncthreads();
+    uint32_t* cur = s0; uint32_t* nxt = s1;
+    if (p.scramble) {
+        // s = in' * prod_j (1 + x^(13*2^j) + x^(14*2^j)) over GF(2), 13*2^j < frame_bits, every frame of the stream in the same round
+        for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
+            for (int i = tid; i < p.frames * fw; i += T4_THREADS) {
+                const int f = i / fw, w = i - f * fw;
+                const uint32_t* cf = cur + f * fw;
+                nxt[i] = cf[w] ^ t4_sm_get32(cf, 32 * w - sh13, fw) ^ t4_sm_get32(cf, 32 * w - sh14, fw);
+            }
+            __syncthreads();
+            uint32_t* t = cur; cur = nxt; nxt = t;
+        }
+    }
+    float2* E = tiles + warp * 32 * T4F_EROW;
+    const float inv_n = 1.f / N;
+    for (int s = warp; s < p.S; s += NW) {
+        const int f = s / p.SpF, sf = s - f * p.SpF;
+        const uint32_t* cf = cur + f * fw;
+        float2 v[32];
+#pragma unroll
+        for (int m1 = 0; m1 < 32; ++m1) {
+            float2 x = make_float2(0.f, 0.f);
+            if (m1 < p.m1n) {
+                const int sl = __ldg(p.slot + 32 * m1 + lane);
+                if (sl >= 0) {
+                    const uint32_t g = t4_sm_get32(cf, (sf * p.Nd + sl) * p.bps, fw);
+                    int idx = 0;
+                    for (int i = 0; i < p.bps; ++i) idx = (idx << 1) | ((g >> i) & 1u);
+                    x = cs[idx];
+                } else if (sl != T4_SLOT_ZERO) {
+                    const float2 pv = __ldg(p.pilots + (int64_t)s * p.Np + (-1 - sl));
+                    x = make_float2(pv.x, -pv.y);
+                }
+            }
+            v[m1] = x;
+        }
+        t4_pass_a(v, E, p.tw_t, lane);
+        fft32<32>(v);
+        float2* dst = out + (b * p.S + s) * (int64_t)(N + p.Tg);
+        const int cp0 = N - p.Tg;
+#pragma unroll
+        for (int j2 = 0; j2 < 32; ++j2) {
+            const int n = lane + 32 * j2;
+            const float2 y = make_float2(v[j2].x * inv_n, -v[j2].y * inv_n);
+            dst[p.Tg + n] = y;
+            if (n >= cp0) dst[n - cp0] = y;
+        }
+    }
+}
+
+const void* t4_twiddle_blob(ofdm_ctx* ctx) {          // [k1][n2] = W1024^{n2 k1}
+    std::vector<float> twt(2 * 1024);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)((n2 * k1) & 1023) / 1024.0L;
+            twt[2 * (32 * k1 + n2)] = (float)cosl(a); twt[2 * (32 * k1 + n2) + 1] = (float)sinl(a);
+        }
+    return ctx_blob(ctx, twt.data(), sizeof(float) * twt.size());
+}
+
+// TX chain fast path for Nfft = 1024 (FP32, every carrier inside N_carrier).  Sets *handled when it ran.
+int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, bool* handled) {
+    *handled = false;
+    if (ctx->precision != OFDM_PREC_F32 || !lp || lp->Nfft != 1024 || getenv("OFDM_B200_NO_FAST")) return OFDM_OK;
+    if (lp->S <= 0 || lp->SpF <= 0 || lp->S % lp->SpF || lp->Nd < 1 || lp->Np < 1 || lp->Tg < 0 || lp->Tg > 1024 || lp->N_carrier < 2 || lp->N_carrier > 1024) return OFDM_OK;
+    ConstTable ct = host_constellation(lp->constellation);
+    if (ct.bps <= 0 || (1 << ct.bps) > 16) return OFDM_OK;
+    std::vector<int32_t> slot(1024, T4_SLOT_ZERO);
+    for (int i = 0; i < lp->Nd; ++i) { const int c = lp->data_carriers_host[i]; if (c < 1 || c > lp->N_carrier) return OFDM_OK; slot[c - 1] = i; }
+    for (int i = 0; i < lp->Np; ++i) { const int c = lp->pilot_carriers_host[i]; if (c < 1 || c > lp->N_carrier) return OFDM_OK; slot[c - 1] = -1 - i; }
+    Tx1024Params p;
+    p.Tg = lp->Tg; p.Nc = lp->N_carrier; p.S = lp->S; p.SpF = lp->SpF; p.Nd = lp->Nd; p.Np = lp->Np; p.bps = ct.bps; p.scramble = lp->scramble;
+    p.frame_bits = lp->SpF * lp->Nd * ct.bps; p.frames = lp->S / lp->SpF; p.m1n = (lp->N_carrier + 31) / 32;
+    p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
+    const int fw = (p.frame_bits + 31) / 32;
+    const size_t smem = sizeof(float2) * (size_t)(T4_THREADS / 32) * 32 * T4F_EROW + 2 * sizeof(uint32_t) * (size_t)p.frames * fw;
+    if (smem > 110 * 1024) return OFDM_OK;            // two CTAs per SM; longer streams take the generic kernel
+    p.slot = (const int32_t*)ctx_blob(ctx, slot.data(), sizeof(int32_t) * slot.size());
+    p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, (size_t)lp->Np * lp->S);
+    p.tw_t = (const float2*)t4_twiddle_blob(ctx);
+    REQUIRE(ctx, p.slot && p.pilots && p.tw_t, "device upload failed");
+    CUDA_TRY(ctx, cudaFuncSetAttribute(tx1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+    tx1024_kernel<<<(unsigned)B, T4_THREADS, smem, ctx->stream>>>(p, make_devconst<float>(lp->constellation), bits, B * stream_bits, (float2*)time);
+    LAUNCH_CHECK(ctx);
+    *handled = true;
+    return OFDM_OK;
+}
+
 extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_t L, int W, int Nfft, void* autocorr, int32_t* tg_pos, double* freq_off,
                                 int32_t* fail);
 

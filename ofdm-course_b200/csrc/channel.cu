@@ -2,6 +2,8 @@
 #include "fft.cuh"
 #include "philox.cuh"
 
+int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* power_sum);
+
 // ---- add_STO (`Task 5/add_STO.m:5-9`)
 template <typename T>
 __global__ void add_sto_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const int32_t* __restrict__ nsto, cx<T>* __restrict__ out) {
@@ -20,33 +22,62 @@ extern "C" int ofdm_add_sto(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L,
     return OFDM_OK;
 }
 
-// ---- add_CFO (`Task 5/add_CFO.m:6-7`): y .* exp(2j*pi*CFO*n/Nfft).  The phase is range-reduced
-// in double (frac of CFO*n/Nfft) so FP32 streams of 64K samples keep full accuracy.
-template <typename T>
-__global__ void add_cfo_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const double* __restrict__ cfo, double inv_nfft,
-                               cx<T>* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * L) return;
-    int64_t b = i / L, n = i - b * L;
-    double ph = cfo[b] * (double)n * inv_nfft;
+// ---- add_CFO (`Task 5/add_CFO.m:6-7`): y .* exp(2j*pi*CFO*n/Nfft).
+// The rotation of sample n is DEFINED here as the double-precision product R(256 (n >> 8)) * R(n & 255), R(k) =
+// exp(2j*pi*frac(CFO*k/Nfft)) with the phase range-reduced in double, rounded to the stream type once: one sincospi per 256
+// samples and per thread instead of one per sample, and the fused Task-4 channel below uses the same definition, so both
+// give identical bits.  (Against the direct evaluation the factor differs by < 3e-16 before the rounding.)
+__device__ __forceinline__ double2 cfo_rot_d(double cfo, double inv_nfft, int64_t k) {
+    double ph = cfo * (double)k * inv_nfft;
     ph -= floor(ph);
-    double s, c;
-    sincospi(2.0 * ph, &s, &c);
-    out[i] = cmul(in[i], mk<T>((T)c, (T)s));
+    double sn, cs;
+    sincospi(2.0 * ph, &sn, &cs);
+    return make_double2(cs, sn);
+}
+// (explicit rounding intrinsics: the contraction into FMAs is pinned, not left to each kernel's optimiser)
+__device__ __forceinline__ float2 cmul_pinned(float2 v, float2 w) {
+    return make_float2(__fmaf_rn(v.x, w.x, -__fmul_rn(v.y, w.y)), __fmaf_rn(v.x, w.y, __fmul_rn(v.y, w.x)));
+}
+__device__ __forceinline__ double2 cmul_pinned(double2 v, double2 w) {
+    return make_double2(__fma_rn(v.x, w.x, -__dmul_rn(v.y, w.y)), __fma_rn(v.x, w.y, __dmul_rn(v.y, w.x)));
+}
+template <typename T>
+__device__ __forceinline__ cx<T> cfo_rot_apply(cx<T> v, double2 rq, double2 rt) {
+    const double2 r = cmul_pinned(rq, rt);
+    return cmul_pinned(v, mk<T>((T)r.x, (T)r.y));
+}
+#define CFO_TILE 2048
+template <typename T>
+__global__ void __launch_bounds__(256) add_cfo_kernel(const cx<T>* __restrict__ in, int64_t L, const double* __restrict__ cfo, double inv_nfft, cx<T>* __restrict__ out) {
+    __shared__ double2 rq[CFO_TILE / 256];
+    const int64_t b = blockIdx.x, n0 = (int64_t)blockIdx.y * CFO_TILE;
+    const double c = cfo[b];
+    if (threadIdx.x < CFO_TILE / 256) rq[threadIdx.x] = cfo_rot_d(c, inv_nfft, n0 + 256 * threadIdx.x);
+    const double2 rt = cfo_rot_d(c, inv_nfft, threadIdx.x);
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < CFO_TILE / 256; ++i) {
+        const int64_t n = n0 + 256 * i + threadIdx.x;
+        if (n < L) out[b * L + n] = cfo_rot_apply<T>(in[b * L + n], rq[i], rt);
+    }
 }
 extern "C" int ofdm_add_cfo(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, const double* cfo, int Nfft, void* out) {
     if (!ctx) return OFDM_ERR_INVALID;
     REQUIRE(ctx, in && out && cfo && B >= 0 && L >= 0 && Nfft > 0, "bad argument");
     if (B * L == 0) return OFDM_OK;
-    DISPATCH_T(ctx, { add_cfo_kernel<T><<<(unsigned)cdiv64(B * L, 256), 256, 0, ctx->stream>>>((const cx<T>*)in, B, L, cfo, 1.0 / Nfft, (cx<T>*)out); });
+    REQUIRE(ctx, cdiv64(L, CFO_TILE) <= 65535, "stream too long");
+    DISPATCH_T(ctx, { add_cfo_kernel<T><<<dim3((unsigned)B, (unsigned)cdiv64(L, CFO_TILE)), 256, 0, ctx->stream>>>((const cx<T>*)in, L, cfo, 1.0 / Nfft, (cx<T>*)out); });
     LAUNCH_CHECK(ctx);
     return OFDM_OK;
 }
 
 // ---- Noise (`Task 5/Noise.m:3-11`): mean power over the whole stream (double), then
 // sqrt(P/2)*(N1 + 1i*N2).  N1/N2 imported (real block, imaginary block) or Philox.
+// Deterministic: block y of stream b writes its partial sum, a second kernel adds the partials in a fixed order (no floating-point
+// atomics: two calls on the same stream give the same sigma to the last bit, in FP64 mode too).
+#define POWER_MAX_BLOCKS 64
 template <typename T>
-__global__ void stream_power_kernel(const cx<T>* __restrict__ in, int64_t L, double* __restrict__ power_sum) {
+__global__ void stream_power_kernel(const cx<T>* __restrict__ in, int64_t L, double* __restrict__ partial) {
     __shared__ double red[32];
     const int64_t b = blockIdx.x;
     double s = 0;
@@ -55,7 +86,14 @@ __global__ void stream_power_kernel(const cx<T>* __restrict__ in, int64_t L, dou
         s += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
     }
     s = block_sum(s, red);
-    if (threadIdx.x == 0) atomicAdd(&power_sum[b], s);
+    if (threadIdx.x == 0) partial[b * gridDim.y + blockIdx.y] = s;
+}
+__global__ void stream_power_finish_kernel(const double* __restrict__ partial, int64_t B, int nb, double* __restrict__ power_sum) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double s = 0;
+    for (int y = 0; y < nb; ++y) s += partial[b * nb + y];
+    power_sum[b] = s;
 }
 template <typename T>
 __global__ void add_noise_kernel(const cx<T>* __restrict__ in, int64_t B, int64_t L, const double* __restrict__ snr_db,
@@ -96,11 +134,11 @@ extern "C" int ofdm_add_noise(ofdm_ctx* ctx, const void* in, int64_t B, int64_t 
     if (B * L == 0) return OFDM_OK;
     double* psum = (double*)ctx_scratch(ctx, sizeof(double) * B);
     REQUIRE(ctx, psum != nullptr, "scratch allocation failed");
-    CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
-    int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
+    {
+        int rc = ofdm_stream_power_sum(ctx, in, B, L, psum);
+        if (rc) return rc;
+    }
     DISPATCH_T(ctx, {
-        stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, psum);
-        ctx->launches++;
         add_noise_kernel<T><<<dim3((unsigned)B, (unsigned)std::min<int64_t>(cdiv64(L, 256 * 4), 256)), 256, 0, ctx->stream>>>(
             (const cx<T>*)in, B, L, snr_db, psum, (const T*)normals, seed, first_stream_id, (cx<T>*)out, nvar);
     });
@@ -204,17 +242,25 @@ __global__ void channel_prep_kernel(int64_t B, int64_t L, const double* __restri
         *nnz = k;
     }
 }
-template <typename T>
+// IMP = true is the Task-4 order (`Task 4/Main_model_Task_4.m:95,103,110,263-264`): Noise -> add_STO -> add_CFO -> multipath.
+// The staged sample m is then  rot(m) * noisy(m + nsto)  (zero where the shifted index leaves the stream, `add_STO.m:5-9`), the
+// Philox normals stay addressed by the ORIGINAL sample index and rot(m) is add_cfo_kernel's two-level rotation: the same
+// bits as ofdm_add_noise -> ofdm_add_sto -> ofdm_add_cfo -> ofdm_apply_fir in one pass over the signal.
+template <typename T, bool IMP>
 __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict__ in, int64_t L, const T* __restrict__ sigma_g, const T* __restrict__ normals,
                                                          uint64_t seed, int64_t first_stream, const cx<T>* __restrict__ hv_g, const int* __restrict__ hd_g,
-                                                         const int* __restrict__ nnz_g, int D, cx<T>* __restrict__ out) {
+                                                         const int* __restrict__ nnz_g, int D, cx<T>* __restrict__ out,
+                                                         const int32_t* __restrict__ nsto_g, const double* __restrict__ cfo_g, double inv_nfft) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cx<T>* sn = (cx<T>*)smem_raw;                   // D - 1 noisy samples of history, then the CH_TILE of the current tile
     cx<T>* hv = sn + CH_TILE + D - 1;               // non-zero taps, ascending delay
     int* hd = (int*)(hv + D);
+    __shared__ double2 rq_s[CH_TILE / 256 + 2];     // IMP: R(256 q) for the q values of the current tile (+ one either side)
     const int64_t b = blockIdx.x;
     const int64_t c0 = (int64_t)blockIdx.y * CH_CHUNK * CH_TILE;    // this CTA walks CH_CHUNK consecutive tiles, carrying the history
     const T sigma = sigma_g[b];
+    const int64_t sto = IMP ? (int64_t)nsto_g[b] : 0;
+    const double cfo = IMP ? cfo_g[b] : 0.0;
     const int nnz = *nnz_g;
     for (int t = threadIdx.x; t < nnz; t += 256) { hv[t] = hv_g[t]; hd[t] = hd_g[t]; }
     const cx<T>* xin = in + b * L;
@@ -236,8 +282,24 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
         v0 = mk<T>(x0.x + sigma * (T)g[0], x0.y + sigma * (T)g[1]);
         if (2 * pr + 1 < L) { const cx<T> x1 = xin[2 * pr + 1]; v1 = mk<T>(x1.x + sigma * (T)g[2], x1.y + sigma * (T)g[3]); }
     };
+    // IMP: staged sample m, evaluated on its own (history of the first tile, and every sample when the normals are imported)
+    auto staged_imp = [&](int64_t m) -> cx<T> {
+        const int64_t q = m + sto;
+        if (m < 0 || m >= L || q < 0 || q >= L) return mk<T>(0, 0);
+        cx<T> v;
+        if (normals) v = noisy_imported(q);
+        else {
+            float g[4];
+            philox_normal_quad(seed, sid, (uint64_t)(q >> 1), g);
+            const cx<T> x = xin[q];
+            v = (q & 1) ? mk<T>(x.x + sigma * (T)g[2], x.y + sigma * (T)g[3]) : mk<T>(x.x + sigma * (T)g[0], x.y + sigma * (T)g[1]);
+        }
+        return cfo_rot_apply<T>(v, cfo_rot_d(cfo, inv_nfft, (m >> 8) << 8), cfo_rot_d(cfo, inv_nfft, m & 255));
+    };
     // history of the first tile: samples c0 - (D-1) .. c0 - 1 (regenerated, not exchanged; c0 is even)
-    if (normals) {
+    if (IMP) {
+        for (int j = threadIdx.x; j < D - 1; j += 256) sn[j] = staged_imp(c0 - (D - 1) + j);
+    } else if (normals) {
         for (int j = threadIdx.x; j < D - 1; j += 256) sn[j] = noisy_imported(c0 - (D - 1) + j);
     } else {
         for (int q = threadIdx.x; 2 * q < D - 1; q += 256) {            // pair c0/2 - 1 - q covers samples c0 - 2q - 2, c0 - 2q - 1
@@ -253,7 +315,42 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
         const int64_t n0 = c0 + (int64_t)tile * CH_TILE;
         if (n0 >= L) break;
         const bool whole = n0 + CH_TILE <= L;               // no range test inside a whole tile
-        if (normals) {
+        if (IMP && normals) {
+#pragma unroll
+            for (int i = 0; i < CH_TILE / 256; ++i) cur[threadIdx.x + 256 * i] = staged_imp(n0 + threadIdx.x + 256 * i);
+        } else if (IMP) {
+            // Philox pairs over the SOURCE index: pair P0 + j holds source samples qb - par + 2 j and the next one, i.e. tile
+            // slots l = 2 j - par and l + 1 (par = parity of qb = n0 + sto); j = 0 .. CH_TILE / 2 covers every slot once.
+            // Slot l of this thread is 2 tid - par + e + 512 i: its (m & 255) part does not depend on i, so the two R(t) are
+            // evaluated once per tile and the R(256 q) come from a small shared table.
+            const int64_t qb = n0 + sto;
+            const int par = (int)(qb & 1);
+            const int64_t P0 = (qb - par) >> 1;
+            __syncthreads();                                 // (rq_s of the previous tile is no longer read)
+            if (threadIdx.x < CH_TILE / 256 + 2) rq_s[threadIdx.x] = cfo_rot_d(cfo, inv_nfft, n0 + 256 * ((int64_t)threadIdx.x - 1));
+            const int la = 2 * (int)threadIdx.x - par;       // slot of element 0 at i = 0 (-1 for thread 0 when par = 1)
+            const double2 rt0 = cfo_rot_d(cfo, inv_nfft, (la) & 255), rt1 = cfo_rot_d(cfo, inv_nfft, (la + 1) & 255);
+            __syncthreads();
+            for (int i = 0; i <= CH_TILE / 512; ++i) {
+                const int j = threadIdx.x + 256 * i;
+                if (j > CH_TILE / 2) break;
+                const int64_t pr = P0 + j;
+                float g[4] = {0.f, 0.f, 0.f, 0.f};
+                if (pr >= 0 && 2 * pr < L) philox_normal_quad(seed, sid, (uint64_t)pr, g);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int l = la + e + 512 * i;
+                    if (l < 0 || l >= CH_TILE) continue;
+                    const int64_t q = 2 * pr + e, m = n0 + l;
+                    cx<T> v = mk<T>(0, 0);
+                    if (q >= 0 && q < L && m < L) {
+                        const cx<T> x = xin[q];
+                        v = cfo_rot_apply<T>(mk<T>(x.x + sigma * (T)g[2 * e], x.y + sigma * (T)g[2 * e + 1]), rq_s[(l >> 8) + 1], e ? rt1 : rt0);
+                    }
+                    cur[l] = v;
+                }
+            }
+        } else if (normals) {
 #pragma unroll
             for (int i = 0; i < CH_TILE / 256; ++i) cur[threadIdx.x + 256 * i] = noisy_imported(n0 + threadIdx.x + 256 * i);
         } else if (whole) {
@@ -317,12 +414,55 @@ __global__ void __launch_bounds__(256) channel_t5_kernel(const cx<T>* __restrict
 
 // sum |x|^2 per stream in double (first half of `Noise.m:3`); also used by ofdm_tx_chain_p for the shapes its fast kernel does not cover
 int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* psum) {
-    CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream));
-    if (B * L == 0) return OFDM_OK;
-    const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), 64);
-    DISPATCH_T(ctx, { stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, psum); });
+    if (B * L == 0) { CUDA_TRY(ctx, cudaMemsetAsync(psum, 0, sizeof(double) * B, ctx->stream)); return OFDM_OK; }
+    const int bx = (int)std::min<int64_t>(cdiv64(L, 256 * 8), POWER_MAX_BLOCKS);
+    double* partial = nullptr;
+    CUDA_TRY(ctx, cudaMallocAsync((void**)&partial, sizeof(double) * (size_t)B * bx, ctx->stream));
+    DISPATCH_T(ctx, { stream_power_kernel<T><<<dim3((unsigned)B, bx), 256, 0, ctx->stream>>>((const cx<T>*)in, L, partial); });
+    ctx->launches++;
+    stream_power_finish_kernel<<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(partial, B, bx, psum);
+    LAUNCH_CHECK(ctx);
+    cudaFreeAsync(partial, ctx->stream);
+    return OFDM_OK;
+}
+
+// Shared launcher of the fused channel kernel.  nsto / cfo NULL: Task-5 order (noise, multipath); both given: Task-4 order.
+static int channel_fused_launch(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const double* power_sum, const void* normals,
+                                uint64_t seed, int64_t first_stream_id, const int32_t* nsto, const double* cfo, int Nfft, const void* h, int D, void* rx) {
+    // scratch: power sums | sigma | compacted taps | their delays | tap count
+    const size_t o_sig = sizeof(double) * (size_t)B, o_hv = o_sig + sizeof(double) * (size_t)B, o_hd = o_hv + sizeof(double2) * (size_t)D,
+                 o_nnz = o_hd + sizeof(int) * (size_t)((D + 3) & ~3);
+    char* scr = (char*)ctx_scratch(ctx, o_nnz + 16);
+    REQUIRE(ctx, scr != nullptr, "scratch allocation failed");
+    const double* psum = power_sum;
+    if (!psum) {                                  // no power handed over by the TX stage: one extra pass over the signal
+        int rc = ofdm_stream_power_sum(ctx, tx, B, L, (double*)scr);
+        if (rc) return rc;
+        psum = (const double*)scr;
+    }
+    const bool imp = nsto != nullptr;
+    DISPATCH_T(ctx, {
+        channel_prep_kernel<T><<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(B, L, snr_db, psum, (const cx<T>*)h, D, (T*)(scr + o_sig), (cx<T>*)(scr + o_hv),
+                                                                                 (int*)(scr + o_hd), (int*)(scr + o_nnz));
+        ctx->launches++;
+        const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + 2 * D - 1) + sizeof(int) * (size_t)D;
+        auto k = imp ? channel_t5_kernel<T, true> : channel_t5_kernel<T, false>;
+        if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<dim3((unsigned)B, (unsigned)cdiv64(L, (int64_t)CH_TILE * CH_CHUNK)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, (const T*)(scr + o_sig), (const T*)normals, seed,
+                                                                                         first_stream_id, (const cx<T>*)(scr + o_hv), (const int*)(scr + o_hd),
+                                                                                         (const int*)(scr + o_nnz), D, (cx<T>*)rx, nsto, cfo, imp ? 1.0 / Nfft : 0.0);
+    });
     LAUNCH_CHECK(ctx);
     return OFDM_OK;
+}
+
+extern "C" int ofdm_channel_t4_p(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const double* power_sum, const void* normals,
+                                 uint64_t seed, int64_t first_stream_id, const int32_t* nsto, const double* cfo, int Nfft, const void* h, int D, void* rx) {
+    if (!ctx) return OFDM_ERR_INVALID;
+    REQUIRE(ctx, tx && rx && snr_db && nsto && cfo && h && B >= 0 && L >= 0 && Nfft > 0 && tx != rx, "bad argument (in-place not supported)");
+    REQUIRE(ctx, D >= 1 && D <= CH_MAXD, "impulse response of 1..1024 samples");
+    if (B * L == 0) return OFDM_OK;
+    return channel_fused_launch(ctx, tx, B, L, snr_db, power_sum, normals, seed, first_stream_id, nsto, cfo, Nfft, h, D, rx);
 }
 
 extern "C" int ofdm_channel_t5(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const void* normals,
@@ -335,32 +475,8 @@ extern "C" int ofdm_channel_t5_p(ofdm_ctx* ctx, const void* tx, int64_t B, int64
     REQUIRE(ctx, tx && rx && B >= 0 && L >= 0, "bad argument");
     if (B * L == 0) return OFDM_OK;
     size_t esz = ctx->precision == OFDM_PREC_F64 ? sizeof(double2) : sizeof(float2);
-    if (snr_db && h && D >= 1 && D <= CH_MAXD && tx != rx) {
-        // scratch: power sums | sigma | compacted taps | their delays | tap count
-        const size_t o_sig = sizeof(double) * (size_t)B, o_hv = o_sig + sizeof(double) * (size_t)B, o_hd = o_hv + sizeof(double2) * (size_t)D,
-                     o_nnz = o_hd + sizeof(int) * (size_t)((D + 3) & ~3);
-        char* scr = (char*)ctx_scratch(ctx, o_nnz + 16);
-        REQUIRE(ctx, scr != nullptr, "scratch allocation failed");
-        const double* psum = power_sum;
-        if (!psum) {                                  // no power handed over by the TX stage: one extra pass over the signal
-            int rc = ofdm_stream_power_sum(ctx, tx, B, L, (double*)scr);
-            if (rc) return rc;
-            psum = (const double*)scr;
-        }
-        DISPATCH_T(ctx, {
-            channel_prep_kernel<T><<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(B, L, snr_db, psum, (const cx<T>*)h, D, (T*)(scr + o_sig), (cx<T>*)(scr + o_hv),
-                                                                                     (int*)(scr + o_hd), (int*)(scr + o_nnz));
-            ctx->launches++;
-            const size_t smem = sizeof(cx<T>) * (size_t)(CH_TILE + 2 * D - 1) + sizeof(int) * (size_t)D;
-            auto k = channel_t5_kernel<T>;
-            if (smem > 48 * 1024) CUDA_TRY(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<dim3((unsigned)B, (unsigned)cdiv64(L, (int64_t)CH_TILE * CH_CHUNK)), 256, smem, ctx->stream>>>((const cx<T>*)tx, L, (const T*)(scr + o_sig), (const T*)normals, seed,
-                                                                                             first_stream_id, (const cx<T>*)(scr + o_hv), (const int*)(scr + o_hd),
-                                                                                             (const int*)(scr + o_nnz), D, (cx<T>*)rx);
-        });
-        LAUNCH_CHECK(ctx);
-        return OFDM_OK;
-    }
+    if (snr_db && h && D >= 1 && D <= CH_MAXD && tx != rx)
+        return channel_fused_launch(ctx, tx, B, L, snr_db, power_sum, normals, seed, first_stream_id, nullptr, nullptr, 0, h, D, rx);
     if (snr_db && h) {
         // noise must precede the filter; stage the noisy stream in a second buffer region
         void* tmp = nullptr;

@@ -153,6 +153,13 @@ extern "C" int ofdm_sweep_ber(ofdm_ctx* ctx, const ofdm_link_params* lp, const o
         REQUIRE(ctx, h_dev != nullptr, "device upload failed");
     }
 
+    const void* unit_tap = nullptr;                                           // "no multipath" for the fused Task-4 channel
+    if (sp->chain == OFDM_SWEEP_TASK4 && !h_dev) {
+        const double one_d[2] = {1.0, 0.0};
+        const float one_f[2] = {1.f, 0.f};
+        unit_tap = ctx->precision == OFDM_PREC_F64 ? ctx_blob(ctx, one_d, sizeof one_d) : ctx_blob(ctx, one_f, sizeof one_f);
+        REQUIRE(ctx, unit_tap != nullptr, "device upload failed");
+    }
     int64_t first = 0, count = 0;
     ofdm_sweep_share((int64_t)sp->n_snr * sp->streams_per_point, sp->rank, sp->world, &first, &count);
     if (count == 0) return OFDM_OK;
@@ -204,14 +211,20 @@ extern "C" int ofdm_sweep_ber(ofdm_ctx* ctx, const ofdm_link_params* lp, const o
             if (rc == OFDM_OK) rc = ofdm_rx_chain_t5(ctx, lp, rx, n, bits, nullptr, nullptr, row, nullptr, sp->near_eps);
         } else {
             // Task 4 order: Noise -> add_STO -> add_CFO -> multipath (`Main_model_Task_4.m:95,103,110,263-264`)
-            rc = ofdm_tx_chain(ctx, &lp_tx, sbits, n, tx);
-            if (rc == OFDM_OK) rc = ofdm_add_noise(ctx, tx, n, L, snr_d, nullptr, sp->seed, g, rx, nullptr);
+            const void* rxs = tx;                                           // where the received streams end up
+            rc = ofdm_tx_chain_p(ctx, &lp_tx, sbits, n, tx, psum);
             if (rc == OFDM_OK) rc = ofdm_draw_sto_cfo(ctx, n, sp->seed, g, sp->sto_max, sp->cfo_int_max, sto_d, cfo_d);
-            if (rc == OFDM_OK) rc = ofdm_add_sto(ctx, rx, n, L, sto_d, tmp);
-            if (rc == OFDM_OK) rc = ofdm_add_cfo(ctx, tmp, n, L, cfo_d, lp->Nfft, h_dev ? rx : tx);
-            if (rc == OFDM_OK && h_dev) rc = ofdm_apply_fir(ctx, rx, n, L, h_dev, D, 0, tx);
-            // `tx` now holds the received streams
-            if (rc == OFDM_OK) rc = ofdm_rx_chain_t4_ex(ctx, lp, tx, n, 1, 1, h_dev ? 1 : 0, bits, nullptr, row, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+            if (rc == OFDM_OK && D <= 1024 && !getenv("OFDM_B200_T4_CHANNEL_COMPOSED")) {
+                // one pass: the four impairments fused (bit-identical to the composition below)
+                rc = ofdm_channel_t4_p(ctx, tx, n, L, snr_d, psum, nullptr, sp->seed, g, sto_d, cfo_d, lp->Nfft, h_dev ? h_dev : unit_tap, h_dev ? D : 1, rx);
+                rxs = rx;
+            } else {
+                if (rc == OFDM_OK) rc = ofdm_add_noise(ctx, tx, n, L, snr_d, nullptr, sp->seed, g, rx, nullptr);
+                if (rc == OFDM_OK) rc = ofdm_add_sto(ctx, rx, n, L, sto_d, tmp);
+                if (rc == OFDM_OK) rc = ofdm_add_cfo(ctx, tmp, n, L, cfo_d, lp->Nfft, h_dev ? rx : tx);
+                if (rc == OFDM_OK && h_dev) rc = ofdm_apply_fir(ctx, rx, n, L, h_dev, D, 0, tx);
+            }
+            if (rc == OFDM_OK) rc = ofdm_rx_chain_t4_ex(ctx, lp, rxs, n, 1, 1, h_dev ? 1 : 0, bits, nullptr, row, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                         sp->near_eps, fail_d);
             if (rc == OFDM_OK) {
                 sum_flags_kernel<<<(unsigned)std::min<int64_t>(cdiv64(n, 256), 64), 256, 0, ctx->stream>>>(fail_d, n, (unsigned long long*)(row + 3));

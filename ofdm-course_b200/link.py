@@ -478,6 +478,23 @@ class Context:
                                              self.p(out)))
         return out.reshape(tx_dev.shape)
 
+    def channel_t4(self, tx_dev, snr_db, nsto, cfo, Nfft, h_dev, normals_dev=None, seed=0, first_stream_id=0, out=None, power_sum=None):
+        """Task-4 channel in one pass: Noise -> add_STO -> add_CFO -> multipath (`Task 4/Main_model_Task_4.m:95,103,110,263-264`);
+        the same bits as add_noise / add_sto / add_cfo / apply_fir called in turn."""
+        x = tx_dev.reshape(tx_dev.shape[0], -1)
+        B, L = x.shape
+        if np.ndim(snr_db) == 0 and not isinstance(snr_db, torch.Tensor):
+            s = torch.full((B,), float(snr_db), dtype=torch.float64, device=self.device)
+        else:
+            s = self.real(np.broadcast_to(np.asarray(snr_db, dtype=np.float64), (B,)).copy())
+        n = nsto if isinstance(nsto, torch.Tensor) else torch.as_tensor(np.broadcast_to(np.asarray(nsto, dtype=np.int32), (B,)).copy(), device=self.device)
+        c = cfo if isinstance(cfo, torch.Tensor) else self.real(np.broadcast_to(np.asarray(cfo, dtype=np.float64), (B,)).copy())
+        if out is None:
+            out = torch.empty_like(x)
+        self._chk(self.lib.ofdm_channel_t4_p(self.h, self.p(x), B, L, self.p(s), self.p(power_sum), self.p(normals_dev), seed, first_stream_id, self.p(n), self.p(c),
+                                             Nfft, self.p(h_dev), h_dev.shape[-1], self.p(out)))
+        return out.reshape(tx_dev.shape)
+
     def rx_chain_t5(self, lp, rx_dev, B, tx_bits_dev=None, want_bits=True, want_H=True, counts=None, near_eps=0.0, want_err_per_stream=False,
                     out_bits=None, H=None):
         if want_bits and out_bits is None:

@@ -616,3 +616,35 @@ def test_rx_chain_task4_split_path_matches_fused_and_oracle(G, monkeypatch):
         assert split["TgPosition"][b].item() == refs[b]["TgPosition"] and split["IFO"][b].item() == refs[b]["IFO"]
     mism = sum(int(np.sum(gs[b] != refs[b]["bits"])) for b in range(len(cases)) if np.all(np.isfinite(refs[b]["H"][:400])))
     assert mism * reps <= 3 * p.bps * int(split["counts"][2].item())
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_channel_t4_fused_is_bit_identical_to_the_composition(G, prec):
+    """ofdm_channel_t4_p (Noise -> add_STO -> add_CFO -> multipath in one pass, `Task 4/Main_model_Task_4.m:95,103,110,263-264`)
+    against ofdm_add_noise / ofdm_add_sto / ofdm_add_cfo / ofdm_apply_fir called in turn: the same bits, for Philox and for
+    imported normals, odd / even / negative / out-of-range offsets, a stream length that is no multiple of the tile."""
+    import torch
+    ctx = G.Context(0, prec)
+    rng = np.random.default_rng(3)
+    B, L, Nfft = 9, 2 * 16384 + 2 * 2048 + 777, 1024
+    x = ctx.cplx(rng.standard_normal((B, L)) + 1j * rng.standard_normal((B, L)))
+    sto = np.array([0, 1, 2, 611, 1152, -3, -40, L + 5, 777], dtype=np.int32)
+    cfo = np.array([0.0, 0.24, -0.5, 3.3, 30.4, 12.5, 7.0, 1.0, 29.99])
+    h = np.zeros(11); h[0], h[4], h[10] = 1.0, 0.6, 0.3
+    hd = ctx.cplx(h.astype(complex))
+    snr = np.linspace(5.0, 30.0, B)
+    for normals in (None, ctx.real(rng.standard_normal((B, 2, L)), ctx.rdtype)):
+        noisy, _ = ctx.add_noise(x, snr, normals_dev=normals, seed=11, first_stream_id=40)
+        ref = ctx.apply_fir(ctx.add_cfo(ctx.add_sto(noisy, sto), cfo, Nfft), hd)
+        got = ctx.channel_t4(x, snr, sto, cfo, Nfft, hd, normals_dev=normals, seed=11, first_stream_id=40)
+        ctx.sync()
+        assert torch.equal(torch.view_as_real(got), torch.view_as_real(ref))
+    one = ctx.cplx(np.ones(1, dtype=complex))
+    got = ctx.channel_t4(x, snr, sto, cfo, Nfft, one, seed=11, first_stream_id=40)
+    ref = ctx.add_cfo(ctx.add_sto(ctx.add_noise(x, snr, seed=11, first_stream_id=40)[0], sto), cfo, Nfft)
+    ctx.sync()
+    assert torch.equal(torch.view_as_real(got), torch.view_as_real(ref))
+    # the rotation itself against the oracle's add_CFO (double): FP32 1e-6 of the sample, FP64 1e-12
+    got = ctx.add_cfo(x, cfo, Nfft).cpu().numpy()
+    want = np.stack([O.add_CFO(x[b].cpu().numpy(), cfo[b], Nfft) for b in range(B)])
+    assert np.max(np.abs(got - want)) < (2e-6 if prec == "f32" else 1e-11)
