@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
 }
 
 int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, double* power_sum);   // channel.cu
-int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, bool* handled);   // chain_rx_t4.cu
+int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, double* power, bool* handled);   // chain_rx_t4.cu
 extern "C" int ofdm_tx_chain(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time) {
     return ofdm_tx_chain_p(ctx, lp, bits, B, time, nullptr);
 }
@@ -346,10 +346,10 @@ extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const 
         if (ctx->precision == OFDM_PREC_F32 && lp && lp->Nfft == 1024) {
             int rc = make_linkdev<float>(ctx, lp, chk);
             if (rc) return rc;
-            rc = ofdm_tx1024_fast(ctx, lp, bits, B, time, &fast);
+            rc = ofdm_tx1024_fast(ctx, lp, bits, B, time, power, &fast);
             if (rc) return rc;
         }
-        if (fast) return power ? ofdm_stream_power_sum(ctx, time, B, (int64_t)lp->S * (lp->Nfft + lp->Tg), power) : OFDM_OK;
+        if (fast) return OFDM_OK;
     }
     DISPATCH_T(ctx, {
         LinkDev<T> d;

@@ -994,25 +994,27 @@ __device__ __forceinline__ uint32_t t4_sm_get32(const uint32_t* w, int pos, int 
     return __funnelshift_r(lo, hi, sh);
 }
 __global__ void __launch_bounds__(T4_THREADS, 2) tx1024_kernel(Tx1024Params p, DevConst<float> con, const uint32_t* __restrict__ bits, int64_t total_bits,
-                                                               float2* __restrict__ out) {
+                                                               float2* __restrict__ out, double* __restrict__ power_part) {
     constexpr int N = 1024;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = T4_THREADS / 32;
     float2* tiles = (float2*)smem_raw;
     const int fw = (p.frame_bits + 31) >> 5;
+    const int fwp = fw + 1;                                    // one zero word after every frame: unconditional two-word bit fetches
     uint32_t* s0 = (uint32_t*)(tiles + NW * 32 * T4F_EROW);
-    uint32_t* s1 = s0 + p.frames * fw;
+    uint32_t* s1 = s0 + p.frames * fwp;
     __shared__ float2 cs[16];                                  // conjugated constellation
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t b = blockIdx.x;
     const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
     if (tid < 16) cs[tid] = make_float2(con.re[tid], -con.im[tid]);
-    for (int i = tid; i < p.frames * fw; i += T4_THREADS) {
-        const int f = i / fw, w = i - f * fw;
+    for (int i = tid; i < p.frames * fwp; i += T4_THREADS) {
+        const int f = i / fwp, w = i - f * fwp;
         const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
-        uint32_t v = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
+        uint32_t v = w < fw ? bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits)) : 0u;
         if (w == 0 && p.scramble) v ^= (p.prev0 >> 19) ^ (p.prev0 >> 18);     // fold the register pre-history into the input
         s0[i] = v;
+        s1[i] = 0u;
     }
     __syncthreads();
     uint32_t* cur = s0; uint32_t* nxt = s1;
@@ -1021,8 +1023,8 @@ __global__ void __launch_bounds__(T4_THREADS, 2) tx1024_kernel(Tx1024Params p, D
         for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
             for (int i = tid; i < p.frames * fw; i += T4_THREADS) {
                 const int f = i / fw, w = i - f * fw;
-                const uint32_t* cf = cur + f * fw;
-                nxt[i] = cf[w] ^ t4_sm_get32(cf, 32 * w - sh13, fw) ^ t4_sm_get32(cf, 32 * w - sh14, fw);
+                const uint32_t* cf = cur + f * fwp;
+                nxt[f * fwp + w] = cf[w] ^ t4_sm_get32(cf, 32 * w - sh13, fw) ^ t4_sm_get32(cf, 32 * w - sh14, fw);
             }
             __syncthreads();
             uint32_t* t = cur; cur = nxt; nxt = t;
@@ -1030,22 +1032,27 @@ __global__ void __launch_bounds__(T4_THREADS, 2) tx1024_kernel(Tx1024Params p, D
     }
     float2* E = tiles + warp * 32 * T4F_EROW;
     const float inv_n = 1.f / N;
+    // roles of this lane's carriers 32 m1 + lane, once for all symbols (only m1 < m1n <= 32 can be occupied)
+    int sl[32];
+#pragma unroll
+    for (int m1 = 0; m1 < 32; ++m1) sl[m1] = m1 < p.m1n ? __ldg(p.slot + 32 * m1 + lane) : T4_SLOT_ZERO;
     for (int s = warp; s < p.S; s += NW) {
         const int f = s / p.SpF, sf = s - f * p.SpF;
-        const uint32_t* cf = cur + f * fw;
+        const uint32_t* cf = cur + f * fwp;
+        const float2* prow = p.pilots + (int64_t)s * p.Np;
         float2 v[32];
+        // all fetches first (independent), the selects after
 #pragma unroll
         for (int m1 = 0; m1 < 32; ++m1) {
             float2 x = make_float2(0.f, 0.f);
             if (m1 < p.m1n) {
-                const int sl = __ldg(p.slot + 32 * m1 + lane);
-                if (sl >= 0) {
-                    const uint32_t g = t4_sm_get32(cf, (sf * p.Nd + sl) * p.bps, fw);
-                    int idx = 0;
-                    for (int i = 0; i < p.bps; ++i) idx = (idx << 1) | ((g >> i) & 1u);
-                    x = cs[idx];
-                } else if (sl != T4_SLOT_ZERO) {
-                    const float2 pv = __ldg(p.pilots + (int64_t)s * p.Np + (-1 - sl));
+                const int r = sl[m1];
+                if (r >= 0) {
+                    const int pos = (sf * p.Nd + r) * p.bps;
+                    const uint32_t g = __funnelshift_r(cf[pos >> 5], cf[(pos >> 5) + 1], pos & 31);
+                    x = cs[__brev(g) >> (32 - p.bps)];                 // the symbol's bits, first bit most significant (`mapping.m`)
+                } else if (r != T4_SLOT_ZERO) {
+                    const float2 pv = __ldg(prow + (-1 - r));
                     x = make_float2(pv.x, -pv.y);
                 }
             }
@@ -1055,12 +1062,19 @@ __global__ void __launch_bounds__(T4_THREADS, 2) tx1024_kernel(Tx1024Params p, D
         fft32<32>(v);
         float2* dst = out + (b * p.S + s) * (int64_t)(N + p.Tg);
         const int cp0 = N - p.Tg;
+        float psym = 0.f;                                      // this lane's share of sum |x|^2 over the symbol, cyclic prefix included
 #pragma unroll
         for (int j2 = 0; j2 < 32; ++j2) {
             const int n = lane + 32 * j2;
             const float2 y = make_float2(v[j2].x * inv_n, -v[j2].y * inv_n);
             dst[p.Tg + n] = y;
             if (n >= cp0) dst[n - cp0] = y;
+            const float e = y.x * y.x + y.y * y.y;
+            psym += n >= cp0 ? e + e : e;
+        }
+        if (power_part) {                                      // `Noise.m:3`: one partial per symbol, added up in symbol order afterwards (deterministic)
+            const double tot = warp_sum((double)psym);
+            if (lane == 0) power_part[b * p.S + s] = tot;
         }
     }
 }
@@ -1076,7 +1090,8 @@ const void* t4_twiddle_blob(ofdm_ctx* ctx) {          // [k1][n2] = W1024^{n2 k1
 }
 
 // TX chain fast path for Nfft = 1024 (FP32, every carrier inside N_carrier).  Sets *handled when it ran.
-int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, bool* handled) {
+int ofdm_power_finish(ofdm_ctx* ctx, const double* partial, int64_t B, int nb, double* power_sum);      // channel.cu
+int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* bits, int64_t B, void* time, double* power, bool* handled) {
     *handled = false;
     if (ctx->precision != OFDM_PREC_F32 || !lp || lp->Nfft != 1024 || getenv("OFDM_B200_NO_FAST")) return OFDM_OK;
     if (lp->S <= 0 || lp->SpF <= 0 || lp->S % lp->SpF || lp->Nd < 1 || lp->Np < 1 || lp->Tg < 0 || lp->Tg > 1024 || lp->N_carrier < 2 || lp->N_carrier > 1024) return OFDM_OK;
@@ -1090,7 +1105,7 @@ int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* 
     p.frame_bits = lp->SpF * lp->Nd * ct.bps; p.frames = lp->S / lp->SpF; p.m1n = (lp->N_carrier + 31) / 32;
     p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
     const int fw = (p.frame_bits + 31) / 32;
-    const size_t smem = sizeof(float2) * (size_t)(T4_THREADS / 32) * 32 * T4F_EROW + 2 * sizeof(uint32_t) * (size_t)p.frames * fw;
+    const size_t smem = sizeof(float2) * (size_t)(T4_THREADS / 32) * 32 * T4F_EROW + 2 * sizeof(uint32_t) * (size_t)p.frames * (fw + 1);
     if (smem > 110 * 1024) return OFDM_OK;            // two CTAs per SM; longer streams take the generic kernel
     p.slot = (const int32_t*)ctx_blob(ctx, slot.data(), sizeof(int32_t) * slot.size());
     p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, (size_t)lp->Np * lp->S);
@@ -1098,10 +1113,16 @@ int ofdm_tx1024_fast(ofdm_ctx* ctx, const ofdm_link_params* lp, const uint32_t* 
     REQUIRE(ctx, p.slot && p.pilots && p.tw_t, "device upload failed");
     CUDA_TRY(ctx, cudaFuncSetAttribute(tx1024_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
-    tx1024_kernel<<<(unsigned)B, T4_THREADS, smem, ctx->stream>>>(p, make_devconst<float>(lp->constellation), bits, B * stream_bits, (float2*)time);
-    LAUNCH_CHECK(ctx);
-    *handled = true;
-    return OFDM_OK;
+    double* part = nullptr;
+    if (power) CUDA_TRY(ctx, cudaMallocAsync((void**)&part, sizeof(double) * (size_t)B * p.S, ctx->stream));
+    tx1024_kernel<<<(unsigned)B, T4_THREADS, smem, ctx->stream>>>(p, make_devconst<float>(lp->constellation), bits, B * stream_bits, (float2*)time, part);
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    int rc = e == cudaSuccess ? OFDM_OK : ctx_fail(ctx, OFDM_ERR_CUDA, "tx1024_kernel launch failed: %s", cudaGetErrorString(e));
+    if (rc == OFDM_OK && power) rc = ofdm_power_finish(ctx, part, B, p.S, power);
+    if (part) cudaFreeAsync(part, ctx->stream);
+    *handled = rc == OFDM_OK;
+    return rc;
 }
 
 extern "C" int ofdm_cp_autocorr(ofdm_ctx* ctx, const void* rx, int64_t B, int64_t L, int W, int Nfft, void* autocorr, int32_t* tg_pos, double* freq_off,

@@ -426,6 +426,13 @@ int ofdm_stream_power_sum(ofdm_ctx* ctx, const void* in, int64_t B, int64_t L, d
     return OFDM_OK;
 }
 
+int ofdm_power_finish(ofdm_ctx* ctx, const double* partial, int64_t B, int nb, double* power_sum) {     // power_sum[b] = partial[b][0] + ... in order
+    if (B == 0) return OFDM_OK;
+    stream_power_finish_kernel<<<(unsigned)cdiv64(B, 256), 256, 0, ctx->stream>>>(partial, B, nb, power_sum);
+    LAUNCH_CHECK(ctx);
+    return OFDM_OK;
+}
+
 // Shared launcher of the fused channel kernel.  nsto / cfo NULL: Task-5 order (noise, multipath); both given: Task-4 order.
 static int channel_fused_launch(ofdm_ctx* ctx, const void* tx, int64_t B, int64_t L, const double* snr_db, const double* power_sum, const void* normals,
                                 uint64_t seed, int64_t first_stream_id, const int32_t* nsto, const double* cfo, int Nfft, const void* h, int D, void* rx) {
