@@ -214,3 +214,126 @@ def test_rx4096_dead_row_mask_and_pass_b_order():
             assert idle == all((dead >> r) & 1 for r in pm[2 * w:2 * w + 2])
     src = _read("chain_rx4096.cu")
     assert "mask_perm(MASK, tid >> 4)" in src and "2 * (tid >> 5) + 1 < mask_popc(MASK)" in src
+
+
+def test_batch_omp_radix16_stockham_passes_and_swizzle():
+    """`od_ifft4096` (sparse_dft.cu): three radix-16 Stockham passes on the conjugate with the pass-1 stores XOR-swizzled
+    inside groups of 16; a numpy model with the kernel's index expressions must give the unnormalised inverse DFT, the
+    swizzled stores / loads must be bank-conflict free per half warp, and pass 3 must leave thread t with l = t + 256 r."""
+    import numpy as np
+    src = _read("sparse_dft.cu")
+    assert "fb[16 * tid + (r ^ (tid & 15))]" in src and "fb[(tid + 256 * q) ^ sw]" in src and "fa + 16 * tid - 15 * k" in src
+    N = 4096
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    tw = np.exp(-2j * np.pi * np.arange(N) / N)
+
+    def twiddled(v, t):
+        wb = [1, tw[t], tw[2 * t], tw[3 * t]]
+        wa = [1, tw[4 * t], tw[8 * t], tw[12 * t]]
+        return np.array([v[q] * wb[q & 3] * wa[q >> 2] for q in range(16)])
+
+    fa, fb = np.conj(x).copy(), np.zeros(N, complex)
+    for t in range(256):
+        V = np.fft.fft(fa[t + 256 * np.arange(16)])
+        for r in range(16):
+            fb[16 * t + (r ^ (t & 15))] = V[r]
+    fa2 = np.zeros(N, complex)
+    for t in range(256):
+        k, sw = t & 15, (t >> 4) & 15
+        V = np.fft.fft(twiddled(np.array([fb[(t + 256 * q) ^ sw] for q in range(16)]), 16 * k))
+        for r in range(16):
+            fa2[16 * t - 15 * k + 16 * r] = V[r]
+    out = np.zeros(N, complex)
+    for t in range(256):
+        V = np.fft.fft(twiddled(fa2[t + 256 * np.arange(16)], t))
+        out[t + 256 * np.arange(16)] = np.conj(V)                   # thread t owns columns t + 256 r
+    assert np.max(np.abs(out - np.fft.ifft(x) * N)) < 1e-9 * N
+    # 8-byte accesses are served per half warp: sixteen lanes must hit sixteen different 8-byte bank pairs
+    for half in range(0, 256, 16):
+        lanes = range(half, half + 16)
+        for r in range(16):
+            assert len({(16 * t + (r ^ (t & 15))) % 16 for t in lanes}) == 16          # pass-1 stores
+        for q in range(16):
+            assert len({((t + 256 * q) ^ ((t >> 4) & 15)) % 16 for t in lanes}) == 16  # pass-2 loads
+            assert len({(16 * t - 15 * (t & 15) + 16 * q) % 16 for t in lanes}) == 16  # pass-2 stores
+
+
+def test_batch_omp_redux_keys_order_like_the_floats():
+    """`od_top2_redux`: |.|^2 >= 0, so bits + 1 is an order-preserving unsigned key, 0 marks "nothing valid" (NaN or -inf
+    never wins); the (max key, min index, max of the rest) triple must equal the shuffle-and-merge top-2 it replaced."""
+    import numpy as np
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([rng.random(200).astype(np.float32), np.float32([0.0, 0.0, 1e-38, 3.4e38, np.inf])])
+    key = lambda v: 0 if not (v >= 0) else int(np.float32(v).view(np.uint32)) + 1
+    order = np.argsort(vals, kind="stable")
+    keys = np.array([key(v) for v in vals], dtype=np.uint64)
+    assert np.all(np.diff(keys[order]) >= 0) and key(np.float32(np.nan)) == 0 and key(np.float32(-np.inf)) == 0
+    for trial in range(200):
+        m = rng.random(64).astype(np.float32)
+        if trial % 3 == 0:
+            m[rng.integers(0, 64, 3)] = m.max()                    # exact ties: the smallest index wins, the runner-up equals the best
+        if trial % 5 == 0:
+            m[rng.integers(0, 64, 5)] = np.nan
+        k = np.array([key(v) for v in m], dtype=np.int64)
+        K1 = k.max(); I1 = int(np.min(np.where(k == K1)[0])); K2 = int(np.max(np.where(np.arange(64) == I1, 0, k)))
+        valid = ~np.isnan(m)
+        best = np.nanmax(m); i_best = int(np.min(np.where(valid & (m == best))[0]))
+        rest = np.where((np.arange(64) != i_best) & valid, m, -np.inf).max()
+        assert I1 == i_best and K1 == key(best) and K2 == key(rest)
+
+
+def test_task4_channel_pair_staging_covers_every_slot_once():
+    """`channel_t5_kernel<T, true>`: Philox pairs are indexed by the SOURCE sample, so a tile of CH_TILE slots starting at
+    source index qb = n0 + sto is covered by pairs P0 + j, j = 0 .. CH_TILE / 2, slot l = 2 j - par + e.  Every slot must be
+    written exactly once, with the source index and the (m & 255) / (m >> 8) rotation parts the kernel assumes."""
+    src = _read("channel.cu")
+    T = _define(src, "CH_TILE")
+    assert "rq_s[(l >> 8) + 1]" in src and "const int la = 2 * (int)threadIdx.x - par;" in src
+    for n0 in (0, T, 5 * T):
+        for sto in (0, 1, 2, 611, -3, -40, 1153):
+            qb = n0 + sto
+            par = qb & 1
+            P0 = (qb - par) >> 1
+            seen = {}
+            for i in range(T // 512 + 1):
+                for tid in range(256):
+                    j = tid + 256 * i
+                    if j > T // 2:
+                        continue
+                    la = 2 * tid - par
+                    for e in (0, 1):
+                        l = la + e + 512 * i
+                        if 0 <= l < T:
+                            assert l not in seen
+                            seen[l] = 2 * (P0 + j) + e
+                            m = n0 + l
+                            assert (m & 255) == ((la + e) & 255) and (m >> 8) == (n0 >> 8) + (l >> 8)
+            assert sorted(seen) == list(range(T))
+            assert all(seen[l] == n0 + l + sto for l in seen)          # slot l holds source sample m + sto
+
+
+def test_two_level_cfo_rotation_is_the_direct_one_to_double_rounding():
+    """`cfo_rot_apply` (channel.cu): rot(n) = R(256 (n >> 8)) * R(n & 255) in double, R(k) = exp(2j pi frac(CFO k / Nfft))."""
+    import numpy as np
+    for cfo in (0.24, -0.5, 3.3, 30.4, 12.5):
+        n = np.arange(0, 57600, 7)
+        R = lambda k: np.exp(2j * np.pi * np.mod(cfo * k / 1024.0, 1.0))
+        two = R(256 * (n >> 8)) * R(n & 255)
+        assert np.max(np.abs(two - np.exp(2j * np.pi * cfo * n / 1024.0))) < 2e-11     # the reference's own phase at n = 57,600 carries 1e-12 of rounding
+
+
+def test_task4_post_kernel_word_decisions_never_straddle_a_symbol():
+    """`t4_post_kernel`: a thread decides the eight consecutive payload symbols of one 32-bit word as two groups of four;
+    with Nd % 4 == 0 a group of four stays inside one OFDM symbol and its equaliser taps are Gd[dr .. dr + 3]."""
+    src = _read("chain_rx_t4.cu")
+    assert "(p.Nd & 3) == 0" in src and "const int dr1 = dr0 + 4 >= p.Nd ? 0 : dr0 + 4;" in src
+    for Nd in (332, 4, 8, 100, 1024):
+        S = 7
+        for w in range(S * Nd // 8):
+            i0 = 8 * w
+            dr0 = i0 % Nd
+            dr1 = 0 if dr0 + 4 >= Nd else dr0 + 4
+            for u in range(8):
+                dr = (dr0 if u < 4 else dr1) + (u & 3)
+                assert dr == (i0 + u) % Nd and dr < Nd
