@@ -549,6 +549,29 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         chk(ofdm_channel_t5(g_ctx, to_dev_complex(A(0), L * B), (int64_t)B, (int64_t)L, snr, NULL, (uint64_t)mxGetScalar(A(3)), 0,
                             D ? to_dev_complex(A(2), D) : NULL, (int)D, rx), op);
         OUT(0, from_dev_complex(rx, L, B));
+    } else if (!strcmp(op, "channel_t4")) {               /* Rx = channel_t4(Tx (L x B), SNR_dB (scalar | 1 x B), STO (scalar | 1 x B), CFO (scalar | 1 x B), Nfft, h (FIR), seed) */
+        NEED(7);                                          /* Noise -> add_STO -> add_CFO -> conv(h), `Task 4/Main_model_Task_4.m:95,103,110,263-264`, in one pass */
+        size_t L = mxGetM(A(0)), B = mxGetN(A(0)), D = mxGetNumberOfElements(A(5)), b, k;
+        double* hd = (double*)hostbuf(B * 8 * 2);
+        int32_t* hs = (int32_t*)hostbuf(B * 4);
+        double* dv[2];
+        int32_t* sto_d;
+        for (k = 1; k <= 3; ++k) {
+            size_t ne = mxGetNumberOfElements(A(k));
+            if (ne != 1 && ne != B) fail("ofdm:channel_t4:arg", "SNR_dB, STO and CFO must be scalars or 1 x B");
+        }
+        if (!D) fail("ofdm:channel_t4:h", "h must hold at least one tap (1 for no multipath)");
+        for (b = 0; b < B; ++b) hd[b] = real_data(A(1))[mxGetNumberOfElements(A(1)) == 1 ? 0 : b];
+        dv[0] = dev_doubles(hd, B);
+        for (b = 0; b < B; ++b) hd[b] = real_data(A(3))[mxGetNumberOfElements(A(3)) == 1 ? 0 : b];
+        dv[1] = dev_doubles(hd, B);
+        for (b = 0; b < B; ++b) hs[b] = (int32_t)real_data(A(2))[mxGetNumberOfElements(A(2)) == 1 ? 0 : b];
+        sto_d = (int32_t*)devbuf(B * 4);
+        chk(ofdm_h2d(g_ctx, sto_d, hs, B * 4), "h2d");
+        void* rx = devbuf(L * B * esz());
+        chk(ofdm_channel_t4_p(g_ctx, to_dev_complex(A(0), L * B), (int64_t)B, (int64_t)L, dv[0], NULL, NULL, (uint64_t)mxGetScalar(A(6)), 0, sto_d, dv[1],
+                              (int)mxGetScalar(A(4)), to_dev_complex(A(5), D), (int)D, rx), op);
+        OUT(0, from_dev_complex(rx, L, B));
     } else if (!strcmp(op, "rx_chain_t5")) {   /* [bits (stream_bits x B), H (N_carrier x B), counts (1 x 3)] = rx_chain_t5(LINK..., Rx (L x B), tx_bits | [], near_eps) */
         NEED(N_LINK + 3);
         ofdm_link_params lp;

@@ -229,6 +229,25 @@ def test_mex_batched_chain_ops_against_oracle(mex):
     assert mism <= 3 * p.bps * counts[0, 2] and abs(counts[0, 0] - ref_err) <= mism
 
 
+def test_mex_channel_t4_against_oracle(mex):
+    """The fused Task-4 channel through the gateway (B = 3 columns) against the oracle's add_STO / add_CFO / conv at an SNR
+    where the noise is far below the comparison tolerance, and its noise level at 15 dB."""
+    rng = np.random.default_rng(23)
+    L, B, Nfft = 6000, 3, 1024
+    tx = rng.standard_normal((L, B)) + 1j * rng.standard_normal((L, B))
+    h, _ = O.get_MP_channel_resp([[0, 1], [4, .6], [10, .3]], Nfft)
+    sto, cfo = np.array([[37.0, 0.0, 900.0]]), np.array([[7.24, -0.3, 12.5]])
+    clean = mex.call("channel_t4", tx, 200.0, sto, cfo, float(Nfft), h, 3.0)
+    for b in range(B):
+        want = O.apply_channel(O.add_CFO(O.add_STO(tx[:, b], sto[0, b]), cfo[0, b], Nfft), h)
+        assert rel(clean[:, b], want) < 2e-6
+    noisy = mex.call("channel_t4", tx, 15.0, sto, cfo, float(Nfft), h, 3.0)
+    for b in range(B):
+        keep = slice(0, L - int(sto[0, b]) - len(h))                       # where the shifted stream has samples
+        snr = 10 * np.log10(np.mean(np.abs(tx[:, b]) ** 2) / np.mean(np.abs((noisy - clean)[keep, b]) ** 2 / np.sum(np.abs(h) ** 2)))
+        assert abs(snr - 15.0) < 0.5
+
+
 def test_mex_sweep_ber(mex):
     """sweep_ber through the gateway == ofdm_sweep_ber through the ctypes binding (same seeds), both chains."""
     import ofdm_b200 as G

@@ -95,6 +95,15 @@ end
     Rx = ofdm_mex('channel_t5', Tx, SNR_dB, h, seed);
 end
 """,
+"ofdm_channel_t4.m": """function Rx = ofdm_channel_t4(Tx, SNR_dB, nSTO, CFO, Nfft, h, seed)
+%OFDM_CHANNEL_T4  Noise -> add_STO -> add_CFO -> multipath for B streams in one pass
+%   (`Task 4/Main_model_Task_4.m:95,103,110,263-264`; the same samples as Noise, add_STO, add_CFO and conv called in turn).
+%   Tx: L x B; SNR_dB, nSTO, CFO: scalars or 1 x B; h: impulse response from get_MP_channel_resp (1 for no multipath);
+%   seed: Philox seed of the noise (stream b uses the counter stream (seed, b-1)).
+    if nargin < 7, seed = 0; end
+    Rx = ofdm_mex('channel_t4', Tx, SNR_dB, nSTO, CFO, Nfft, h, seed);
+end
+""",
 "ofdm_rx_chain_t5.m": """function [bits, H, counts] = ofdm_rx_chain_t5(P, Rx, tx_bits, near_eps)
 %OFDM_RX_CHAIN_T5  OFDM_demodulator -> LS_CE -> equalize_signal -> get_payload -> demapping -> DeScrambler -> BER count
 %   for B streams in one pass (`Task 5/Task5_part2.m:169-174,269-303`).  Rx: L x B host matrix (the library chunks and
