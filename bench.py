@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--streams", type=int, default=65536, help="streams per GPU per step (M1: 65,536 = 917,504 symbols)")
     ap.add_argument("--e2e-streams", type=int, default=8192)
     ap.add_argument("--m5-streams", type=int, default=8192, help="streams per SNR point of the Task-5 sweep record (0 = skip)")
-    ap.add_argument("--m5-streams-t4", type=int, default=2048, help="streams per SNR point of the Task-4 (STO/CFO) sweep record (0 = skip)")
+    ap.add_argument("--m5-streams-t4", type=int, default=8192, help="streams per SNR point of the Task-4 (STO/CFO) sweep record (0 = skip)")
     ap.add_argument("--m5-tile", type=int, default=8192)
     ap.add_argument("--e2e-chunk", type=int, default=512)
     ap.add_argument("--ref-streams", type=int, default=200, help="distinct streams per host process in the CPU sample")
