@@ -23,7 +23,7 @@ static void (*g_atexit)(void) = NULL;
 mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c) {
     mxArray* a = (mxArray*)calloc(1, sizeof(mxArray));
     a->m = m; a->n = n; a->is_complex = (c == mxCOMPLEX);
-    size_t cnt = m * n ? m * n : 1;
+    size_t cnt = (m != 0 && n != 0) ? m * n : 1;
 #ifdef OFDM_MEX_SPLIT_COMPLEX
     a->re = (double*)calloc(cnt, sizeof(double));
     if (a->is_complex) a->im = (double*)calloc(cnt, sizeof(double));
