@@ -531,7 +531,7 @@ def test_fused_kernels_are_deterministic_across_launches(G):
 
 
 def test_persistent_wraparound_against_oracle(G):
-    """B = 640 streams > 2 x 148 persistent CTAs: every CTA of tx4096 / channel_t5 / rx4096 walks at least two streams, so the
+    """B = 640 streams > 2 x 148 (tx4096) and > 3 x 148 (three-CTA rx4096) persistent CTAs: CTAs walk on to a second stream, so the
     prefetch cursor's stream-to-stream hop (`pf_advance`) and the per-stream state resets are compared with the oracle --
     TX samples, channel output with imported normals, channel estimate, decided bits and per-stream error counts, for all
     640 streams (the oracle's vectorised scrambler forms are bit-identical to its loops, `test_oracle_kats`)."""
@@ -648,3 +648,34 @@ def test_channel_t4_fused_is_bit_identical_to_the_composition(G, prec):
     got = ctx.add_cfo(x, cfo, Nfft).cpu().numpy()
     want = np.stack([O.add_CFO(x[b].cpu().numpy(), cfo[b], Nfft) for b in range(B)])
     assert np.max(np.abs(got - want)) < (2e-6 if prec == "f32" else 1e-11)
+
+
+def test_rx4096_three_cta_kernel_against_the_two_cta_kernel(G, monkeypatch):
+    """The three-CTA (`SLIM`) instantiation of rx4096_kernel -- one landing buffer, L2 prefetch, two-factor twiddles -- against
+    the two-CTA one on 1,000 streams (CTAs of both walk over two or three streams): channel estimates to FP32 tolerance, the
+    same error counts per stream except where a symbol sits within the counted near-boundary margin."""
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    B = 1000
+    import torch
+    g = torch.Generator(device=ctx.device); g.manual_seed(5)
+    bd = torch.randint(-2**31, 2**31 - 1, (B * p.stream_bits // 32,), dtype=torch.int32, device=ctx.device, generator=g)
+    tx, ps = ctx.tx_chain(lp, bd, B, want_power=True)
+    rx = ctx.channel_t5(tx, snr_db=13.0, h_dev=ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0]), seed=3, power_sum=ps)
+    l0 = ctx.launches
+    slim = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd, near_eps=1e-3, want_err_per_stream=True)
+    ctx.sync()
+    monkeypatch.setenv("OFDM_B200_NO_SLIM", "1")
+    two = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd, near_eps=1e-3, want_err_per_stream=True)
+    ctx.sync()
+    assert ctx.launches - l0 == 2
+    Hs, Ht = slim["H"].cpu().numpy(), two["H"].cpu().numpy()
+    assert np.max(np.abs(Hs - Ht)) < 2e-6 * np.max(np.abs(Ht))
+    cs, ct = slim["counts"].cpu().numpy(), two["counts"].cpu().numpy()
+    assert cs[1] == ct[1] == B * p.stream_bits and cs[0] > 0
+    bs = ctx.host_bits(slim["bits"], B * p.stream_bits)
+    bt = ctx.host_bits(two["bits"], B * p.stream_bits)
+    assert int(np.sum(bs != bt)) <= p.bps * int(cs[2] + ct[2])
+    es, et = slim["err_per_stream"].cpu().numpy(), two["err_per_stream"].cpu().numpy()
+    assert int(es.sum()) == cs[0] and int(et.sum()) == ct[0] and int(np.sum(np.abs(es - et))) <= p.bps * int(cs[2] + ct[2])
