@@ -389,6 +389,37 @@ def test_omp_random_pilots_large_dictionary(G):
     assert list(idx) == list(idx_ref) and rel_err(H, H_ref) < 1e-4
 
 
+@pytest.mark.parametrize("Nfft,Ldict,Np", [(4096, 3000, 256), (4096, 777, 200), (2048, 2048, 128), (2048, 1500, 128), (1024, 600, 64)])
+def test_batch_omp_partial_dictionaries(G, Nfft, Ldict, Np):
+    """Batch-OMP kernel on dictionaries that do not fill the thread grid (Ldict < 256 NG: the masked argmax branch) and on the
+    smaller transforms (Nfft 1024 / 2048 take the shared-memory FFT, 4096 the register radix-16 one), 12 frames each, taps
+    inside and near the end of the dictionary, against the oracle's OMP_estimate."""
+    rng = np.random.default_rng(Nfft + Ldict)
+    pil = np.sort(rng.permutation(Nfft // 4)[:Np]) + 1
+    A = O.sensing_matrix_dft(pil, Nfft, Ldict)
+    B, K = 12, 6
+    ys, refs = [], []
+    for b in range(B):
+        h = np.zeros(Nfft, dtype=complex)
+        taps = np.concatenate([rng.choice(Ldict - 40, 3, replace=False), [Ldict - 1 - b, Ldict - 17]])
+        h[taps] = crandn(rng, 5) * np.array([1, .8, .6, .5, .4])
+        y = np.fft.fft(h)[pil - 1] + 0.01 * crandn(rng, Np)
+        ys.append(y)
+        refs.append(O.OMP_estimate(y, A, Nfft, K, 20))
+    ctx = G.default_context("f32")
+    l0 = ctx.launches
+    H, h, idx, it, near = ctx.omp(ctx.cplx(np.stack(ys)), Nfft, K, Ldict=Ldict, pilot_loc=pil, tie_eps=1e-4)
+    ctx.sync()
+    assert ctx.launches - l0 == 2                       # Gram vector + the fused Batch-OMP kernel
+    for b in range(B):
+        n = int(it[b])
+        if int(near[b]) == 0:
+            assert list(idx[b, :n].cpu().numpy()) == list(refs[b][2]), b
+            assert rel_err(h[b].cpu().numpy(), refs[b][1]) < 2e-4 and rel_err(H[b].cpu().numpy(), refs[b][0]) < 2e-4
+        assert int(idx[b, :n].max()) <= Ldict
+    assert int((near > 0).sum()) <= 2
+
+
 # ------------------------------------------------------------------ a24/a25
 def test_ber_mer(G):
     rng = np.random.default_rng(37)
