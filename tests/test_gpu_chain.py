@@ -679,3 +679,55 @@ def test_rx4096_three_cta_kernel_against_the_two_cta_kernel(G, monkeypatch):
     assert int(np.sum(bs != bt)) <= p.bps * int(cs[2] + ct[2])
     es, et = slim["err_per_stream"].cpu().numpy(), two["err_per_stream"].cpu().numpy()
     assert int(es.sum()) == cs[0] and int(et.sum()) == ct[0] and int(np.sum(np.abs(es - et))) <= p.bps * int(cs[2] + ct[2])
+
+
+@pytest.mark.parametrize("ncar,tg,con", [(400, 128, "16QAM"), (1000, 256, "QPSK"), (100, 0, "8PSK"), (416, 64, "BPSK")])
+def test_tx1024_fast_kernel_variants(G, monkeypatch, ncar, tg, con):
+    """The warp-per-symbol TX kernel of the Nfft = 1024 shape (`tx1024_kernel`) on other carrier counts (up to 32 carrier
+    groups per lane), guard lengths and constellations: against the oracle's TX chain, against the generic kernel, and
+    scrambling inside the kernel against ofdm_scramble followed by the kernel without it (bit-identical)."""
+    import torch
+    p = OC.LinkParams(Nfft=1024, N_carrier=ncar, T_Guard=tg, Amount_OFDM_Frames=4, Amount_ODFM_SpF=3, Constellation=con)
+    p.pilotCarriers, p.dataCarriers = O.pilot_layout_percent(p.N_carrier, 15, p.Nfft, last_gap=2)
+    p.pilotValues, _ = OC.make_pilot_values(len(p.pilotCarriers), p.N_symb, p.Constellation, 4 / 3, True)
+    ctx = G.default_context("f32")
+    lp, lp_raw = _lp(ctx, p), _lp(ctx, p, scramble=False)
+    rng = np.random.default_rng(ncar + tg)
+    B = 5
+    bits = rng.integers(0, 2, (B, p.stream_bits)).astype(np.uint8)
+    bd = ctx.bits(bits.ravel())
+    l0 = ctx.launches
+    tx, ps = ctx.tx_chain(lp, bd, B, want_power=True)
+    ctx.sync()
+    assert ctx.launches - l0 == 2                       # tx1024_kernel + the ordered sum of its per-symbol power partials
+    tx_h = tx.cpu().numpy().reshape(B, -1)
+    for b in range(B):
+        ref, _, _ = OC.tx_chain(p, bits[b], fast=True)
+        assert rel_err(tx_h[b], ref) < 2e-6, b
+        assert abs(ps[b].item() / np.sum(np.abs(ref) ** 2) - 1) < 1e-5
+    if p.stream_bits % 32 == 0 and p.frame_bits >= 15:
+        sb = ctx.scramble(bd, B * p.Amount_OFDM_Frames, p.frame_bits) if p.frame_bits % 32 == 0 else None
+        if sb is not None:
+            assert torch.equal(torch.view_as_real(ctx.tx_chain(lp_raw, sb, B)), torch.view_as_real(tx))
+    monkeypatch.setenv("OFDM_B200_NO_FAST", "1")
+    gen = ctx.tx_chain(lp, bd, B).cpu().numpy().reshape(B, -1)
+    assert rel_err(gen, tx_h) < 2e-6
+
+
+def test_channel_t4_long_impulse_response_and_short_streams(G):
+    """ofdm_channel_t4_p at the corners of its staging: an impulse response as long as a third of a tile (history regenerated
+    through the per-sample path), streams shorter than one tile, one stream -- still the bits of the four calls."""
+    import torch
+    ctx = G.default_context("f32")
+    rng = np.random.default_rng(8)
+    for B, L, D in ((1, 777, 300), (3, 2048, 700), (2, 2049, 1), (4, 5000, 1024)):
+        x = ctx.cplx(rng.standard_normal((B, L)) + 1j * rng.standard_normal((B, L)))
+        h = rng.standard_normal(D) * (rng.random(D) < 0.2)
+        h[0] = 1.0
+        hd = ctx.cplx(h.astype(complex))
+        sto = rng.integers(-50, 400, B).astype(np.int32)
+        cfo = rng.random(B) * 20 - 0.5
+        ref = ctx.apply_fir(ctx.add_cfo(ctx.add_sto(ctx.add_noise(x, 12.0, seed=2, first_stream_id=9)[0], sto), cfo, 1024), hd)
+        got = ctx.channel_t4(x, 12.0, sto, cfo, 1024, hd, seed=2, first_stream_id=9)
+        ctx.sync()
+        assert torch.equal(torch.view_as_real(got), torch.view_as_real(ref)), (B, L, D)
