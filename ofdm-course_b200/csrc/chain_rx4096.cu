@@ -439,10 +439,14 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     if (q16 && (dead & 0x1111) == 0x1111) {      // comb 4, 4m
         if (slim) kern = near ? rx4096_kernel<true, true, 0x1111, true> : rx4096_kernel<true, false, 0x1111, true>;
         else kern = near ? rx4096_kernel<true, true, 0x1111, false> : rx4096_kernel<true, false, 0x1111, false>;
-    } else if (q16 && (dead & 0x0101) == 0x0101) kern = near ? rx4096_kernel<true, true, 0x0101, false> : rx4096_kernel<true, false, 0x0101, false>;  // comb 8, 8m
-    else kern = q16 ? (near ? rx4096_kernel<true, true, 0, false> : rx4096_kernel<true, false, 0, false>)
-                    : (near ? rx4096_kernel<false, true, 0, false> : rx4096_kernel<false, false, 0, false>);
-    const bool use_slim = slim && q16 && (dead & 0x1111) == 0x1111;
+    } else if (q16 && (dead & 0x0101) == 0x0101) {   // comb 8, 8m
+        if (slim) kern = near ? rx4096_kernel<true, true, 0x0101, true> : rx4096_kernel<true, false, 0x0101, true>;
+        else kern = near ? rx4096_kernel<true, true, 0x0101, false> : rx4096_kernel<true, false, 0x0101, false>;
+    } else if (q16) {                                // any other 16QAM layout: no dead rows
+        if (slim) kern = near ? rx4096_kernel<true, true, 0, true> : rx4096_kernel<true, false, 0, true>;
+        else kern = near ? rx4096_kernel<true, true, 0, false> : rx4096_kernel<true, false, 0, false>;
+    } else kern = near ? rx4096_kernel<false, true, 0, false> : rx4096_kernel<false, false, 0, false>;
+    const bool use_slim = slim && q16;
     if (use_slim) smem = smem_slim;
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * (use_slim ? 3 : 2));
