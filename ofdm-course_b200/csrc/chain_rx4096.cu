@@ -35,7 +35,8 @@ __device__ __forceinline__ void stg_once(uint32_t* p, uint32_t v) { asm volatile
 __device__ __forceinline__ void stg_once(float2* p, float2 v) { asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory"); }
 
 struct Fast4096Params {
-    int Tg, S, SpF, Nc, Nd, Np, frame_words, frames, scramble, con_id;
+    int Tg, S, SpF, Nc, Nd, Np, frame_words, frames, scramble, con_id;   // frame_words = ceil(frame_bits / 32)
+    int frame_bits, aligned;   // aligned: frame_bits % 32 == 0 (every frame and stream starts on a word of the packed bit arrays)
     uint32_t prev0;
     const int32_t* slot;       // 1024 entries for carriers 0..1023 (data rank / -1-pilot / SLOT_ZERO)
     const float2* pilots;      // Np (first symbol column)
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
     const int tid = threadIdx.x;
     const int bps = con.bps;
     for (int i = tid; i < 1024; i += FX_THREADS) slot_s[i] = p.slot[i];
+    if (tid < 8) symidx[p.SpF * p.Nd + tid] = 0;          // padding read by the last (partial) word of an unaligned frame
     for (int i = tid; i < p.Np; i += FX_THREADS) { float2 x = p.pilots[i]; float dd = x.x * x.x + x.y * x.y; pinv[i] = make_float2(x.x / dd, -x.y / dd); }
 
     // per-thread twiddles, resident for the whole kernel.  SLIM keeps W^{t c}, W^{4 t d} (c, d = 1..3) per pass and multiplies
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
             }
         }
         uint32_t txw[4] = {0u, 0u, 0u, 0u};
-        if (!SLIM && sf == p.SpF - 1 && txbits) {  // reference words of this frame, consumed ~400 instructions later
+        if (!SLIM && sf == p.SpF - 1 && txbits && p.aligned) {  // reference words of this frame, consumed ~400 instructions later
             const uint32_t* tp = txbits + b * stream_words + (int64_t)f * p.frame_words + tid;
 #pragma unroll
             for (int j = 0; j < 4; ++j) if (tid + FX_THREADS * j < p.frame_words) txw[j] = ldg_once(tp + FX_THREADS * j);
@@ -330,7 +332,42 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
             }
         }
         // ---- frame complete: pack, DeScrambler, compare (reference words were prefetched before pass C's tail)
-        if (sf == p.SpF - 1) {
+        if (sf == p.SpF - 1 && !p.aligned) {
+            // frames that do not end on a word boundary (e.g. comb 7: 24,556 bits): same packing and descrambling per frame word,
+            // the last word masked to the frame, reference bits fetched / decided bits OR-ed in at the frame's bit offset of the
+            // packed arrays (out_bits is zeroed by the host entry); the decisions buffer carries eight zero bytes of padding
+            __syncthreads();
+            const int64_t stream_bits = (int64_t)p.frame_bits * p.frames;
+            const int64_t fbase = b * stream_bits + (int64_t)f * p.frame_bits;
+            auto packed = [&](int w) -> uint32_t {
+                if (QAM16) {
+                    const uint2 by = *reinterpret_cast<const uint2*>(symidx + 8 * w);
+                    uint32_t lo = by.x | (by.x >> 4); lo = (lo & 0xFFu) | ((lo >> 8) & 0xFF00u);
+                    uint32_t hi = by.y | (by.y >> 4); hi = (hi & 0xFFu) | ((hi >> 8) & 0xFF00u);
+                    return lo | (hi << 16);
+                }
+                uint32_t word = 0;
+                const int b0 = 32 * w, b1 = min(b0 + 32, p.frame_bits);
+                for (int j = b0 / bps; j * bps < b1; ++j) {
+                    int idx = symidx[j];
+                    for (int i = 0; i < bps; ++i) {
+                        int pos = j * bps + i;
+                        if (pos >= b0 && pos < b1 && ((idx >> (bps - 1 - i)) & 1)) word |= 1u << (pos - b0);
+                    }
+                }
+                return word;
+            };
+            for (int w = tid; w < p.frame_words; w += FX_THREADS) {
+                const uint32_t cw = packed(w);
+                uint32_t o = cw;
+                if (p.scramble) { const uint32_t prev = w ? packed(w - 1) : p.prev0; o = cw ^ ((cw << 13) | (prev >> 19)) ^ ((cw << 14) | (prev >> 18)); }
+                const int n = min(32, p.frame_bits - 32 * w);
+                if (n < 32) o &= (1u << n) - 1u;
+                if (txbits) errs += __popc(o ^ bits_get32(txbits, fbase + 32 * (int64_t)w, fbase + p.frame_bits));
+                if (outbits) bits_put(outbits, fbase + 32 * (int64_t)w, n, o);
+            }
+            __syncthreads();                       // the decisions buffer is rewritten by the next frame
+        } else if (sf == p.SpF - 1) {
             __syncthreads();
             const int64_t wbase = b * stream_words + (int64_t)f * p.frame_words;
             auto packed = [&](int w) -> uint32_t {
@@ -385,7 +422,7 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
                 const int wn = warp_sum(nears);
                 if ((tid & 31) == 0 && wn && counts) atomicAdd(&counts[2], (unsigned long long)wn);
             }
-            if (tid == 0 && counts) atomicAdd(&counts[1], (unsigned long long)(stream_words * 32));
+            if (tid == 0 && counts) atomicAdd(&counts[1], (unsigned long long)((int64_t)p.frame_bits * p.frames));
             errs = 0; nears = 0; s = 0; sf = 0; sfNd = 0; f = 0;
             b += gridDim.x;
         }
@@ -399,7 +436,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     ConstTable ct = host_constellation(lp->constellation);
     if (ct.bps == 0 || lp->S <= 0 || lp->SpF <= 0 || lp->S % lp->SpF) return OFDM_OK;
     const int frame_bits = lp->SpF * lp->Nd * ct.bps;
-    if (frame_bits % 32 != 0 || lp->Np < 2 || lp->Nd < 1) return OFDM_OK;       // unaligned frames take the generic kernel
+    if (lp->Np < 2 || lp->Nd < 1) return OFDM_OK;
     if (getenv("OFDM_B200_NO_FAST")) return OFDM_OK;
     std::vector<int32_t> slot(1024, SLOT_ZERO);
     for (int i = 0; i < lp->Nd; ++i) { int c = lp->data_carriers_host[i]; if (c < 1 || c > lp->N_carrier) return OFDM_OK; slot[c - 1] = i; }
@@ -412,7 +449,8 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     REQUIRE(ctx, pl != nullptr, "plan construction failed");
     Fast4096Params p;
     p.Tg = lp->Tg; p.S = lp->S; p.SpF = lp->SpF; p.Nc = lp->N_carrier; p.Nd = lp->Nd; p.Np = lp->Np;
-    p.frame_words = frame_bits / 32; p.frames = lp->S / lp->SpF; p.scramble = lp->scramble; p.con_id = lp->constellation;
+    p.frame_words = (frame_bits + 31) / 32; p.frames = lp->S / lp->SpF; p.scramble = lp->scramble; p.con_id = lp->constellation;
+    p.frame_bits = frame_bits; p.aligned = frame_bits % 32 == 0;
     p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
     p.slot = (const int32_t*)ctx_blob(ctx, slot.data(), sizeof(int32_t) * 1024);
     p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, lp->Np);
@@ -423,7 +461,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     if (lp->Tg & 1) return OFDM_OK;          // bulk copies need 16-byte aligned symbol starts
     if (((uintptr_t)rx) & 15) return OFDM_OK;
     size_t smem = sizeof(float2) * (2 * XBUF + 1024 + 2 * (size_t)pl->n_knots) + sizeof(int32_t) * 1024 +
-                  (size_t)lp->SpF * lp->Nd + sizeof(float2) * (size_t)lp->Np + 32;
+                  (size_t)lp->SpF * lp->Nd + 8 + sizeof(float2) * (size_t)lp->Np + 32;
     if (smem > 110 * 1024) return OFDM_OK;   // keep two CTAs per SM; odd shapes take the generic kernel
     const bool q16 = lp->constellation == OFDM_16QAM;
     const bool near = near_eps > 0.0;
@@ -451,6 +489,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<int64_t>(B, (int64_t)ctx->sm_count * (use_slim ? 3 : 2));
     if (err_stream) CUDA_TRY(ctx, cudaMemsetAsync(err_stream, 0, sizeof(int32_t) * B, ctx->stream));
+    if (out_bits && !p.aligned) CUDA_TRY(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t) * OFDM_BIT_WORDS(B * (int64_t)frame_bits * p.frames), ctx->stream));
     DevConst<float> con = make_devconst<float>(lp->constellation);
     PlanDev<float> pd = plan_dev<float>(pl);
     kern<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream,

@@ -731,3 +731,33 @@ def test_channel_t4_long_impulse_response_and_short_streams(G):
         got = ctx.channel_t4(x, 12.0, sto, cfo, 1024, hd, seed=2, first_stream_id=9)
         ctx.sync()
         assert torch.equal(torch.view_as_real(got), torch.view_as_real(ref)), (B, L, D)
+
+
+def test_rx4096_unaligned_frames_at_a_large_batch(G):
+    """comb 7 (frames of 24,556 bits, streams of 49,112: neither ends on a word): 500 streams through the fast kernels -- stream
+    and frame boundaries fall inside words of the packed bit arrays that two CTAs write -- loop-back without impairments must
+    return every bit, and with noise the per-stream error counts must add up to the counter."""
+    p = OC.params_task5(comb=7)
+    assert p.frame_bits % 32 != 0 and p.stream_bits % 32 != 0
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    rng = np.random.default_rng(7)
+    B = 500
+    bits = rng.integers(0, 2, B * p.stream_bits).astype(np.uint8)
+    bd = ctx.bits(bits)
+    tx = ctx.tx_chain(lp, bd, B)
+    l0 = ctx.launches
+    res = ctx.rx_chain_t5(lp, tx, B, tx_bits_dev=bd, want_err_per_stream=True)
+    ctx.sync()
+    assert ctx.launches - l0 == 1                       # the fast kernel, not the generic one
+    counts = res["counts"].cpu().numpy()
+    assert counts[0] == 0 and counts[1] == B * p.stream_bits
+    assert np.array_equal(ctx.host_bits(res["bits"], B * p.stream_bits), bits)
+    rx = ctx.channel_t5(tx, snr_db=12.0, h_dev=ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0]), seed=4)
+    res = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd, want_err_per_stream=True)
+    ctx.sync()
+    got = ctx.host_bits(res["bits"], B * p.stream_bits)
+    counts = res["counts"].cpu().numpy()
+    eps = res["err_per_stream"].cpu().numpy()
+    per_stream = (got != bits).reshape(B, -1).sum(axis=1)
+    assert counts[0] == per_stream.sum() > 0 and np.array_equal(eps, per_stream)
