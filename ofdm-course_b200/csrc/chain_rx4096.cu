@@ -36,6 +36,7 @@ __device__ __forceinline__ void stg_once(float2* p, float2 v) { asm volatile("st
 
 struct Fast4096Params {
     int Tg, S, SpF, Nc, Nd, Np, frame_words, frames, scramble, con_id;   // frame_words = ceil(frame_bits / 32)
+    int txpf;                  // SLIM: prefetch the frame's reference words into L2 (off: OFDM_B200_NO_TXPF)
     int frame_bits, aligned;   // aligned: frame_bits % 32 == 0 (every frame and stream starts on a word of the packed bit arrays)
     uint32_t prev0;
     const int32_t* slot;       // 1024 entries for carriers 0..1023 (data rank / -1-pilot / SLOT_ZERO)
@@ -281,6 +282,10 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
                 pf_advance();
             }
         }
+        // SLIM has no registers to hold the frame's reference words across pass C: pull them into L2 one symbol before the
+        // frame ends instead, so the compare at the frame end waits for L2, not for HBM (16-byte granules only)
+        if (SLIM && tid == 0 && txbits && p.txpf && sf == (p.SpF > 1 ? p.SpF - 2 : 0))
+            bulk_prefetch_l2(txbits + b * stream_words + (int64_t)f * p.frame_words, (uint32_t)p.frame_words * 4u);
         uint32_t txw[4] = {0u, 0u, 0u, 0u};
         if (!SLIM && sf == p.SpF - 1 && txbits && p.aligned) {  // reference words of this frame, consumed ~400 instructions later
             const uint32_t* tp = txbits + b * stream_words + (int64_t)f * p.frame_words + tid;
@@ -451,6 +456,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     p.Tg = lp->Tg; p.S = lp->S; p.SpF = lp->SpF; p.Nc = lp->N_carrier; p.Nd = lp->Nd; p.Np = lp->Np;
     p.frame_words = (frame_bits + 31) / 32; p.frames = lp->S / lp->SpF; p.scramble = lp->scramble; p.con_id = lp->constellation;
     p.frame_bits = frame_bits; p.aligned = frame_bits % 32 == 0;
+    p.txpf = p.aligned && (p.frame_words & 3) == 0 && (((uintptr_t)tx_bits) & 15) == 0 && !getenv("OFDM_B200_NO_TXPF");
     p.prev0 = ofdm_reg_to_prev(lp->reg0_host);
     p.slot = (const int32_t*)ctx_blob(ctx, slot.data(), sizeof(int32_t) * 1024);
     p.pilots = (const float2*)ofdm_upload_pilots(ctx, lp->pilot_vals_host, lp->Np);
