@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(CH_THREADS) tx_chain_kernel(LinkDev<T> p, cons
 #define TXF_XBUF 4128
 #define TXF_PAD(fw) ((fw) + ((fw) >> 3) + 2)
 __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p, const uint32_t* __restrict__ bits, int64_t total_bits, float2* __restrict__ out,
-                                                               double* __restrict__ power, int64_t B) {
+                                                               double* __restrict__ power, int64_t B, unsigned long long* __restrict__ next_stream) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xb = (float2*)smem_raw;                       // two transform buffers
     const int fw = (p.frame_bits + 31) >> 5;
@@ -193,7 +193,14 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
     };
     if ((int64_t)blockIdx.x < B) fetch_frame(blockIdx.x, 0);
     // persistent CTA: the per-thread twiddles, slot roles and the constellation table above are set up once for all its streams
-    for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    // With a scheduling counter the CTA's first stream is blockIdx.x and every further one is claimed from the counter (no tail,
+    // no lock-step imbalance); the claim is made at the start of the current stream because its last frame already fetches the
+    // first frame of the next one.  Two slots by stream parity: the next claim never overwrites a slot still being read.
+    __shared__ long long s_next[2];
+    int kpar = 0;
+    for (int64_t b = blockIdx.x; b < B;) {
+        if (next_stream && tid == 0) s_next[kpar] = (long long)gridDim.x + (long long)atomicAdd(next_stream, 1ull);
+        int64_t bnext = b + gridDim.x;
         double pacc = 0.0;                                    // this thread's share of sum |x|^2 over the stream, cyclic prefixes included
         for (int f = 0; f < p.frames; ++f) {
             const int64_t base = b * stream_bits + (int64_t)f * p.frame_bits;
@@ -205,8 +212,9 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
             }
             for (int w = tid + 3 * CH_THREADS; w < fw; w += CH_THREADS) s0[w] = bits_get32(bits, base + 32 * (int64_t)w, min(total_bits, base + p.frame_bits));
             __syncthreads();
+            if (next_stream) bnext = s_next[kpar];            // (written before this frame's barriers)
             if (f + 1 < p.frames) fetch_frame(b, f + 1);
-            else if (b + gridDim.x < B) fetch_frame(b + gridDim.x, 0);
+            else if (bnext < B) fetch_frame(bnext, 0);
             uint32_t* cur = s0; uint32_t* nxt = s1;
             if (p.scramble) {
                 for (int sh13 = 13, sh14 = 14; sh13 < p.frame_bits; sh13 <<= 1, sh14 <<= 1) {
@@ -311,6 +319,8 @@ __global__ void __launch_bounds__(CH_THREADS, 2) tx4096_kernel(LinkDev<float> p,
             const double tot = block_sum(pacc, red);
             if (tid == 0) power[b] = tot;
         }
+        b = bnext;
+        kpar ^= 1;
     }
 }
 
@@ -334,8 +344,14 @@ extern "C" int ofdm_tx_chain_p(ofdm_ctx* ctx, const ofdm_link_params* lp, const 
         const size_t smem = sizeof(float2) * 2 * TXF_XBUF + 2 * sizeof(uint32_t) * (size_t)(fw + TXF_PAD(fw));   // two bit arrays + their zero pads
         if (ok && smem <= 110 * 1024) {
             CUDA_TRY(ctx, cudaFuncSetAttribute(tx4096_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            tx4096_kernel<<<(unsigned)std::min<int64_t>(B, 2 * (int64_t)ctx->sm_count), CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames,
-                                                                                                                   (float2*)time, power, B);
+            const int64_t grid = std::min<int64_t>(B, 2 * (int64_t)ctx->sm_count);
+            unsigned long long* sched = nullptr;                  // per launch: launches on different streams may overlap
+            if (B > grid && !getenv("OFDM_B200_STATIC_STREAMS")) {
+                CUDA_TRY(ctx, cudaMallocAsync((void**)&sched, sizeof(unsigned long long), ctx->stream));
+                CUDA_TRY(ctx, cudaMemsetAsync(sched, 0, sizeof(unsigned long long), ctx->stream));
+            }
+            tx4096_kernel<<<(unsigned)grid, CH_THREADS, smem, ctx->stream>>>(d, bits, B * (int64_t)d.frame_bits * d.frames, (float2*)time, power, B, sched);
+            if (sched) cudaFreeAsync(sched, ctx->stream);
             LAUNCH_CHECK(ctx);
             return OFDM_OK;
         }

@@ -101,7 +101,7 @@ template <bool QAM16, bool NEAR, int MASK, bool SLIM>
 __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
                                                                float2* __restrict__ Hout, unsigned long long* __restrict__ counts,
-                                                               int32_t* __restrict__ err_stream, float near_eps) {
+                                                               int32_t* __restrict__ err_stream, float near_eps, unsigned long long* __restrict__ next_stream) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[2];
     float2* xb0 = (float2*)smem_raw;            // two 4096-sample symbol buffers (ring)
@@ -198,10 +198,18 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
     int sfNd = 0;                                  // sf * Nd: row of the frame's decision buffer this symbol fills
     int64_t b = blockIdx.x;
     uint32_t parity = 0;
-    for (int64_t q = 0; q < n_items; ++q) {
+    // SLIM with a scheduling counter: a CTA's first stream is blockIdx.x, every further one is claimed from the counter (no
+    // tail: the last streams go to whichever CTAs are free).  The claim for the NEXT stream is made on symbol 0 of the current
+    // one, so that the copy / L2 prefetch of its first symbols can be issued on time; all threads pick it up at the stream end.
+    __shared__ long long s_bnext[2];                   // double-buffered by stream parity: the next claim never overwrites a slot still being read
+    int kpar = 0;
+    const bool dyn = SLIM && next_stream != nullptr;
+    int64_t bn = dyn ? B : b + gridDim.x;              // thread 0's copy of the next stream (B = none)
+    for (int64_t q = 0; dyn ? (b < B) : (q < n_items); ++q) {
         const int cur = SLIM ? 0 : (int)(q & 1);
         float2* X = xb0 + cur * XBUF;
         float2 v[16];
+        if (dyn && s == 0 && tid == 0) { bn = (int64_t)gridDim.x + (int64_t)atomicAdd(next_stream, 1ull); s_bnext[kpar] = bn; }
         mbar_wait(&bars[cur], parity);
         parity ^= SLIM ? 1u : (uint32_t)cur;       // flips after every buffer has been used once
 #pragma unroll
@@ -266,17 +274,16 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
             }
         }
         __syncthreads();                           // buffer `cur` is free: refill it with item q+2
-        if (tid == 0 && q + (SLIM ? 1 : 2) < n_items) {
+        if (tid == 0 && (SLIM ? (s + 1 < p.S || bn < B) : (q + 2 < n_items))) {
             fence_proxy_async();
             mbar_expect_tx(&bars[cur], 32768u);
             if (SLIM) {     // the item after this one: next symbol of the stream, or symbol 0 of this CTA's next stream (no carried cursor)
                 const bool wrap = s + 1 == p.S;
-                const float2* nxt = rx + (b + (wrap ? (int64_t)gridDim.x : 0)) * stream_stride + (int64_t)(wrap ? 0 : s + 1) * symlen + p.Tg;
+                const float2* nxt = rx + (wrap ? bn : b) * stream_stride + (int64_t)(wrap ? 0 : s + 1) * symlen + p.Tg;
                 bulk_g2s(X, nxt, 32768u, &bars[cur]);
-                if (q + 2 < n_items) {      // and the one after that into L2: with a single buffer the copy above is on the critical path
-                    const int s2 = s + 2 >= p.S ? s + 2 - p.S : s + 2;
-                    bulk_prefetch_l2(rx + (b + (s + 2 >= p.S ? (int64_t)gridDim.x : 0)) * stream_stride + (int64_t)s2 * symlen + p.Tg, 32768u);
-                }
+                // and the one after that into L2: with a single buffer the copy above is on the critical path
+                if (s + 2 < p.S) bulk_prefetch_l2(rx + b * stream_stride + (int64_t)(s + 2) * symlen + p.Tg, 32768u);
+                else if (bn < B && s + 2 - p.S < p.S) bulk_prefetch_l2(rx + bn * stream_stride + (int64_t)(s + 2 - p.S) * symlen + p.Tg, 32768u);
             } else {
                 bulk_g2s(X, pf_ptr, 32768u, &bars[cur]);
                 pf_advance();
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast40
             }
             if (tid == 0 && counts) atomicAdd(&counts[1], (unsigned long long)((int64_t)p.frame_bits * p.frames));
             errs = 0; nears = 0; s = 0; sf = 0; sfNd = 0; f = 0;
-            b += gridDim.x;
+            if (dyn) { b = s_bnext[kpar]; kpar ^= 1; } else { b += gridDim.x; bn = b + gridDim.x; }
         }
     }
 }
@@ -476,7 +483,7 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     for (int k = 0; k < 1024; ++k) if (slot[k] >= 0) dead &= ~(1 << (k & 15));
     if (getenv("OFDM_B200_NO_PRUNE")) dead = 0;
     typedef void (*kern_t)(Fast4096Params, PlanDev<float>, DevConst<float>, const float2*, int64_t, const uint32_t*, uint32_t*, float2*, unsigned long long*,
-                           int32_t*, float);
+                           int32_t*, float, unsigned long long*);
     kern_t kern;
     const size_t smem_slim = smem - sizeof(float2) * XBUF;
     const bool slim = getenv("OFDM_B200_NO_SLIM") == nullptr && smem_slim <= 74 * 1024;
@@ -498,8 +505,15 @@ int ofdm_rx_chain_fast4096(ofdm_ctx* ctx, const ofdm_link_params* lp, const void
     if (out_bits && !p.aligned) CUDA_TRY(ctx, cudaMemsetAsync(out_bits, 0, sizeof(uint32_t) * OFDM_BIT_WORDS(B * (int64_t)frame_bits * p.frames), ctx->stream));
     DevConst<float> con = make_devconst<float>(lp->constellation);
     PlanDev<float> pd = plan_dev<float>(pl);
+    // the three-CTA kernel claims its streams from a counter (per launch: two launches may be in flight on different streams)
+    unsigned long long* sched = nullptr;
+    if (use_slim && B > grid && !getenv("OFDM_B200_STATIC_STREAMS")) {
+        CUDA_TRY(ctx, cudaMallocAsync((void**)&sched, sizeof(unsigned long long), ctx->stream));
+        CUDA_TRY(ctx, cudaMemsetAsync(sched, 0, sizeof(unsigned long long), ctx->stream));
+    }
     kern<<<grid, FX_THREADS, smem, ctx->stream>>>(p, pd, con, (const float2*)rx, B, tx_bits, out_bits, (float2*)H, (unsigned long long*)counts, err_stream,
-                                                  (float)near_eps);
+                                                  (float)near_eps, sched);
+    if (sched) cudaFreeAsync(sched, ctx->stream);
     LAUNCH_CHECK(ctx);
     *handled = true;
     return OFDM_OK;
