@@ -337,3 +337,39 @@ def test_task4_post_kernel_word_decisions_never_straddle_a_symbol():
             for u in range(8):
                 dr = (dr0 if u < 4 else dr1) + (u & 3)
                 assert dr == (i0 + u) % Nd and dr < Nd
+
+
+def test_dynamic_stream_claims_cover_every_stream_once_and_never_clobber_a_live_slot():
+    """Persistent kernels (`rx4096_kernel` SLIM, `tx4096_kernel`): CTA c starts on stream c; on symbol 0 of every stream its
+    thread 0 claims the next one (grid + atomicAdd) into slot `parity of the stream count`, the other threads read that slot
+    at the stream end.  A randomised interleaving of CTAs must process every stream exactly once, and a slot must not be
+    rewritten between its write and the stream end that reads it."""
+    import random
+    for fn in ("chain_rx4096.cu", "chain.cu"):
+        src = _read(fn)
+        assert "atomicAdd(next_stream, 1ull)" in src and "kpar ^= 1" in src
+    rnd = random.Random(3)
+    for grid, B in ((444, 65536), (296, 300), (7, 7), (5, 23)):
+        counter = 0
+        done = []
+        # per-CTA state: current stream, phase (0 = at symbol 0, 1 = at stream end), slots, parity, slot "live" flags
+        ctas = [{"b": c, "phase": 0, "slot": [None, None], "live": [False, False], "k": 0} for c in range(min(grid, B))]
+        active = list(range(len(ctas)))
+        while active:
+            c = rnd.choice(active)
+            st = ctas[c]
+            if st["phase"] == 0:                      # symbol 0: claim the next stream
+                assert not st["live"][st["k"]]        # the slot written now is not awaited by a pending read
+                st["slot"][st["k"]] = grid + counter
+                st["live"][st["k"]] = True
+                counter += 1
+                st["phase"] = 1
+            else:                                     # stream end: everybody reads the slot
+                done.append(st["b"])
+                st["b"] = st["slot"][st["k"]]
+                st["live"][st["k"]] = False
+                st["k"] ^= 1
+                st["phase"] = 0
+                if st["b"] >= B:
+                    active.remove(c)
+        assert sorted(done) == list(range(B))
