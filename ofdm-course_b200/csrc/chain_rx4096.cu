@@ -96,7 +96,7 @@ __host__ __device__ constexpr int mask_perm(int m, int j) {
 // SLIM: three CTAs per SM instead of two.  One symbol buffer per CTA (the next symbol is fetched as soon as pass C has read
 // the current one, and lands during pass C's arithmetic, the decisions and whatever the two co-resident CTAs are doing) and
 // two-level twiddles: W^{t k1} = W^{t (k1 & 3)} * W^{4 t (k1 >> 2)} from six resident values per pass instead of fifteen,
-// at the price of nine extra complex multiplications per pass -- 85 registers and 61 KB of shared memory per CTA.
+// at the price of nine extra complex multiplications per pass -- 80 registers and 61 KB of shared memory per CTA.
 template <bool QAM16, bool NEAR, int MASK, bool SLIM>
 __global__ void __launch_bounds__(FX_THREADS, SLIM ? 3 : 2) rx4096_kernel(Fast4096Params p, PlanDev<float> plan, DevConst<float> con, const float2* __restrict__ rx,
                                                                int64_t B, const uint32_t* __restrict__ txbits, uint32_t* __restrict__ outbits,
