@@ -761,3 +761,32 @@ def test_rx4096_unaligned_frames_at_a_large_batch(G):
     eps = res["err_per_stream"].cpu().numpy()
     per_stream = (got != bits).reshape(B, -1).sum(axis=1)
     assert counts[0] == per_stream.sum() > 0 and np.array_equal(eps, per_stream)
+
+
+def test_dynamic_stream_claims_give_the_bits_of_the_static_stride(G, monkeypatch):
+    """rx4096 (three-CTA) and tx4096 claim their streams from a per-launch counter; which CTA processes a stream must not
+    matter: 1,000 streams, every output bit-identical to the static-stride schedule."""
+    import torch
+    p = OC.params_task5(comb=4)
+    ctx = G.default_context("f32")
+    lp = _lp(ctx, p)
+    B = 1000
+    g = torch.Generator(device=ctx.device); g.manual_seed(11)
+    bd = torch.randint(-2**31, 2**31 - 1, (B * p.stream_bits // 32,), dtype=torch.int32, device=ctx.device, generator=g)
+    hd = ctx.cplx(O.get_MP_channel_resp(TAPS5, p.Nfft)[0])
+
+    def run():
+        tx, ps = ctx.tx_chain(lp, bd, B, want_power=True)
+        rx = ctx.channel_t5(tx, snr_db=12.0, h_dev=hd, seed=3, power_sum=ps)
+        res = ctx.rx_chain_t5(lp, rx, B, tx_bits_dev=bd, near_eps=1e-3, want_err_per_stream=True)
+        ctx.sync()
+        return tx, ps, res
+
+    tx_d, ps_d, dyn = run()
+    monkeypatch.setenv("OFDM_B200_STATIC_STREAMS", "1")
+    tx_s, ps_s, sta = run()
+    assert torch.equal(torch.view_as_real(tx_d), torch.view_as_real(tx_s)) and torch.equal(ps_d, ps_s)
+    for key in ("bits", "H", "counts", "err_per_stream"):
+        a, b = dyn[key], sta[key]
+        assert torch.equal(torch.view_as_real(a) if a.is_complex() else a, torch.view_as_real(b) if b.is_complex() else b), key
+    assert int(dyn["counts"][0]) > 0
