@@ -59,3 +59,18 @@ def test_product_never_imports_oracle():
     for fn in os.listdir(pkg):
         if fn.endswith(".py"):
             assert "oracle" not in re.sub(r'""".*?"""', "", open(os.path.join(pkg, fn)).read(), flags=re.S).replace("no CPU fallback", "")
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """INTEGRATION.md section 8 lists the diagnostic switches: every getenv("OFDM_B200_...") in the CUDA sources must appear there
+    (and nothing documented may have vanished from the sources)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    used = set()
+    for f in glob.glob(os.path.join(root, "ofdm-course_b200", "csrc", "*.cu")) + glob.glob(os.path.join(root, "ofdm-course_b200", "csrc", "*.cuh")):
+        used |= set(re.findall(r'getenv\("(OFDM_B200_[A-Z0-9_]+)"\)', open(f).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    section = doc[doc.index("## 8. Diagnostic switches"):]
+    documented = set(re.findall(r"`(OFDM_B200_[A-Z0-9_]+)`", section))
+    assert used == documented, (sorted(used - documented), sorted(documented - used))
